@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Throughput of the LCT hot path on B200 (BASELINE.json metric: LCT transients/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one LCT forward over one batch of synthetic transients.  At N = 1 the
+workload is BASELINE.json configs[1]'s LCT part: batch 8 x 1 x 256 x 64 x 64 per GPU
+(`--workload cfg3|cfg4|cfg5` selects the other shapes).  N > 1 shards by transient:
+every rank runs the same per-GPU batch (weak scaling), no data-path collective.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` is the
+same metric through the public module API with pinned-host input and host output
+inside the timed region; `roofline` is the dominant kernel's algorithmic bytes over
+its CUDA-event duration against MEASURED_PEAKS.json; `cpu_baseline` is the CPU
+oracle port (oracle/lct_oracle.py, the reference's op sequence) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+WORKLOADS = {
+    # name: (per-GPU batch, M, N, description)
+    "cfg2": (8, 256, 64, "LCT forward, batch 8 x 1 x 256x64x64 per GPU (BASELINE.json configs[1], LCT part)"),
+    "cfg3": (8, 512, 128, "LCT forward, batch 8 x 1 x 512x128x128 per GPU (configs[2] at 8 GPUs)"),
+    "cfg4": (16, 128, 128, "LCT forward, batch 16 x 1 x 128x128x128 per GPU (configs[3], LCT part)"),
+    "cfg5": (1, 512, 256, "LCT forward, single 512x256x256 transient (configs[4])"),
+    "tiny": (2, 64, 16, "LCT forward, batch 2 x 1 x 64x16x16 (harness self-test)"),
+}
+STAGES = ("time_fwd", "row_fwd", "col_filter", "row_inv", "time_inv")
+
+
+def bin_len_for(M):
+    return 0.01 * 512 / M          # trange = 5.12 as in the released configs
+
+
+def stage_bytes(M, N, C):
+    """Algorithmic bytes per launch of each kernel (DESIGN.md 'Kernels')."""
+    V = M * N * N
+    return [12 * V * C, 24 * V * C, 32 * V * C + 32 * V, 24 * V * C, 12 * V * C]
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _once(self):
+        nv = self.nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+        for bit, name in names.items():
+            if r & bit:
+                self.reasons.add(name)
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self._once()
+            except Exception:
+                return
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=1.0)
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(statistics.median(self.samples)), "sm_max_mhz": float(self.max_mhz),
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_oracle_rate(M, N, reps, warm, threads=None):
+    """Transients/s of the CPU oracle port on one transient of the workload's shape."""
+    from oracle.lct_oracle import LctOracle
+    if threads:
+        torch.set_num_threads(threads)
+    orc = LctOracle(N, M, bin_len_for(M))
+    torch.manual_seed(410)
+    x = torch.rand(1, 1, M, N, N)
+    times = []
+    with torch.no_grad():
+        for i in range(warm + reps):
+            t0 = time.perf_counter()
+            orc.forward(x, [0], [M])
+            if i >= warm:
+                times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args, rank):
+    """`--impl reference`: the reference's own CPU implementation of the path (the oracle port:
+    /root/reference cannot travel to the GPU box) on the host cores; rank 0 only."""
+    if rank != 0:
+        return
+    B, M, N, desc = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    times = cpu_oracle_rate(M, N, args.steps, args.warmup, threads=cores)
+    total = sum(times)
+    value = len(times) / total
+    line = {
+        "impl": "reference", "metric": "lct_transients_per_sec_fwd", "value": value, "unit": "transients/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "B": B, "M": M, "N": N},
+        "cpu_baseline": {"value": value, "unit": "transients/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"one 1x1x{M}x{N}x{N} transient of the workload per step, forward, torch CPU fp32, "
+                                   f"{torch.get_num_threads()} threads"},
+        "e2e": {"value": value, "unit": "transients/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-reps", type=int, default=60)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    import hiddenpose_b200 as hp
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, M, N, desc = WORKLOADS[args.workload]
+    K, W = args.steps, args.warmup
+    layer = hp.lct(spatial=N, crop=M, bin_len=bin_len_for(M), wall_size=2.0, method="lct", material="diffuse")
+    layer.todev(dev, 1)
+    plan = layer._plan
+    torch.manual_seed(410 + rank)
+    x = torch.rand(B, 1, M, N, N, device=dev)
+    tbes, tens = [0] * B, [M] * B
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def new_events(n):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+        for e in evs:
+            e.record()              # instantiates the underlying cudaEvent_t
+        return evs
+
+    # ---- forward, device-resident, per-stage events inside the timed region ----------------
+    with torch.no_grad():
+        for _ in range(W):
+            y = layer(x, tbes, tens)
+        torch.cuda.synchronize()
+        stage_events = [new_events(6) for _ in range(K)]
+        sampler = ClockSampler(local_rank)
+        barrier()
+        sampler.start()
+        for i in range(K):
+            flush.zero_()
+            y = plan.run_staged(x, tbes, tens, M, stage_events[i], backward=False)
+        barrier()
+        clocks = sampler.stop()
+    step_ms = [ev[0].elapsed_time(ev[5]) for ev in stage_events]
+    stage_ms = [[ev[j].elapsed_time(ev[j + 1]) for ev in stage_events] for j in range(5)]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = world * B * K / (total_ms * 1e-3)
+
+    # ---- forward + backward (autograd through the module), device-resident -----------------
+    xg = x.clone().requires_grad_(True)
+    g = torch.randn(B, 1, M, N, N, device=dev)
+    for _ in range(W):
+        layer(xg, tbes, tens).backward(g)
+        xg.grad = None
+    fb_events = [new_events(2) for _ in range(K)]
+    barrier()
+    for i in range(K):
+        flush.zero_()
+        fb_events[i][0].record()
+        layer(xg, tbes, tens).backward(g)
+        fb_events[i][1].record()
+        xg.grad = None
+    barrier()
+    fb_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in fb_events)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(fb_ms, op=dist.ReduceOp.MAX)
+    fb_ms = float(fb_ms.item())
+
+    # ---- end to end: pinned host input -> H2D -> forward -> D2H of the volume, every step ---
+    x_host = x.cpu().pin_memory()
+    y_host = torch.empty(B, 1, M, N, N).pin_memory()
+    xd = torch.empty_like(x)
+    with torch.no_grad():
+        for _ in range(W):
+            xd.copy_(x_host, non_blocking=True)
+            y_host.copy_(layer(xd, tbes, tens), non_blocking=True)
+        e2e_ev = new_events(2)
+        barrier()
+        e2e_ev[0].record()
+        for _ in range(K):
+            xd.copy_(x_host, non_blocking=True)
+            y_host.copy_(layer(xd, tbes, tens), non_blocking=True)
+        e2e_ev[1].record()
+        barrier()
+    e2e_ms = torch.tensor([e2e_ev[0].elapsed_time(e2e_ev[1])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / (float(e2e_ms.item()) * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        C = B
+        sb = stage_bytes(M, N, C)
+        mean_stage = [statistics.fmean(v) for v in stage_ms]
+        stages = [{"kernel": STAGES[j], "ms": mean_stage[j], "bytes": sb[j],
+                   "gbs": sb[j] / (mean_stage[j] * 1e-3) / 1e9, "frac": sb[j] / (mean_stage[j] * 1e-3) / 1e9 / peak,
+                   "share": mean_stage[j] / sum(mean_stage)} for j in range(5)]
+        top = max(range(5), key=lambda j: mean_stage[j])
+        chain_bytes = sum(sb)
+        chain_gbs = chain_bytes / (statistics.fmean(step_ms) * 1e-3) / 1e9
+        line = {
+            "metric": "lct_transients_per_sec_fwd", "value": value, "unit": "transients/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "B_per_gpu": B, "M": M, "N": N, "seed": 410,
+                       "l2": "flushed between timed steps (512 MiB write outside the events)",
+                       "timing": "CUDA events per step on the launch stream, sum over K steps, max over ranks"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "transients/s", "h2d_bytes_per_step": x.numel() * 4,
+                    "d2h_bytes_per_step": y.numel() * 4,
+                    "how": "module API: pinned x -> H2D -> lct.forward -> D2H of the volume, every step, one stream"},
+            "gpu_launches": 5 * K,
+            "fwd_bwd": {"value": world * B * K / (fb_ms * 1e-3), "unit": "transients/s", "ms_per_step": fb_ms / K,
+                        "gpu_launches": 10 * K},
+            "roofline": {"bound": "hbm", "kernel": STAGES[top], "achieved": stages[top]["gbs"], "peak": peak,
+                         "unit": "GB/s", "frac": stages[top]["frac"], "traffic": None, "peak_source": peak_src,
+                         "chain": {"bytes": chain_bytes, "gbs": chain_gbs, "frac": chain_gbs / peak}},
+            "stages": stages,
+        }
+        if not args.no_cpu_baseline:
+            times = cpu_oracle_rate(M, N, args.cpu_reps, 2)
+            line["cpu_baseline"] = {
+                "value": 1.0 / statistics.median(times), "unit": "transients/s", "cores": torch.get_num_threads(),
+                "kind": "port",
+                "sample": f"{args.cpu_reps} forwards of one 1x1x{M}x{N}x{N} transient (oracle port of tflct.py:94-179, "
+                          f"torch CPU fp32), median; host has {os.cpu_count()} logical cores"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,142 @@
+// Plan selection and the five-kernel chain, shared by the CUDA library
+// (lct_api.cu) and by the CPU thread emulator used in tests (tests/emu).
+#pragma once
+
+#include "lct_kernels.cuh"
+
+namespace lct {
+
+// Column-batched plans (lanes run across columns; used along T with L = M and
+// along H with L = 2N).
+template <int L> struct ColPlan;
+template <> struct ColPlan<16>  { using type = Plan<4, 4>; };
+template <> struct ColPlan<32>  { using type = Plan<8, 4>; };
+template <> struct ColPlan<64>  { using type = Plan<8, 8>; };
+template <> struct ColPlan<128> { using type = Plan<16, 8>; };
+template <> struct ColPlan<256> { using type = Plan<16, 16>; };
+template <> struct ColPlan<512> { using type = Plan<8, 8, 8>; };
+
+// Line plans for K3 (lanes run along the contiguous line): two stages only.
+template <int L> struct LinePlan;
+template <> struct LinePlan<16>  { using type = Plan<4, 4>; };
+template <> struct LinePlan<32>  { using type = Plan<8, 4>; };
+template <> struct LinePlan<64>  { using type = Plan<8, 8>; };
+template <> struct LinePlan<128> { using type = Plan<16, 8>; };
+template <> struct LinePlan<256> { using type = Plan<16, 16>; };
+template <> struct LinePlan<512> { using type = Plan<32, 16>; };
+
+// column tile (in columns of the flattened H*W axis) for the T-axis kernels
+template <int M> struct TimeTile { static constexpr int CT = (M >= 512) ? 16 : 32; };
+// column tile along W for the H-axis kernels
+template <int N> struct RowTile { static constexpr int CT = (N >= 256) ? 16 : (N < 32 ? N : 32); };
+// rows per block for K3
+template <int N> struct LineRows {
+    using P = typename LinePlan<2 * N>::type;
+    static constexpr int RB = (256 / P::TL) < 2 * N ? (256 / P::TL) : 2 * N;
+};
+
+constexpr bool supported_M(int M) { return M == 32 || M == 64 || M == 128 || M == 256 || M == 512; }
+constexpr bool supported_N(int N) { return N == 8 || N == 16 || N == 32 || N == 64 || N == 128 || N == 256; }
+
+enum ChainStage { kStageTimeFwd = 1, kStageRowFwd = 2, kStageColFilter = 4, kStageRowInv = 8, kStageTimeInv = 16, kStageAll = 31 };
+
+template <int M, class Launcher> int launch_time_fwd(const Params& p, Launcher& l) {
+    return l.template launch<TimeFwd<typename ColPlan<M>::type, TimeTile<M>::CT>>(p);
+}
+template <int M, class Launcher> int launch_time_inv(const Params& p, Launcher& l) {
+    return l.template launch<TimeInv<typename ColPlan<M>::type, TimeTile<M>::CT>>(p);
+}
+template <int N, class Launcher> int launch_row_fwd(const Params& p, Launcher& l) {
+    return l.template launch<RowFwd<typename ColPlan<2 * N>::type, RowTile<N>::CT>>(p);
+}
+template <int N, class Launcher> int launch_row_inv(const Params& p, Launcher& l) {
+    return l.template launch<RowInv<typename ColPlan<2 * N>::type, RowTile<N>::CT>>(p);
+}
+template <int N, class Launcher> int launch_col_filter(const Params& p, Launcher& l) {
+    return l.template launch<ColFilter<typename LinePlan<2 * N>::type, LineRows<N>::RB>>(p);
+}
+
+#define LCT_SWITCH_M(M, CALL)                                   \
+    switch (M) {                                                \
+        case 32:  { constexpr int kM = 32;  rc = CALL; } break; \
+        case 64:  { constexpr int kM = 64;  rc = CALL; } break; \
+        case 128: { constexpr int kM = 128; rc = CALL; } break; \
+        case 256: { constexpr int kM = 256; rc = CALL; } break; \
+        case 512: { constexpr int kM = 512; rc = CALL; } break; \
+        default: rc = -1;                                       \
+    }
+#define LCT_SWITCH_N(N, CALL)                                   \
+    switch (N) {                                                \
+        case 8:   { constexpr int kN = 8;   rc = CALL; } break; \
+        case 16:  { constexpr int kN = 16;  rc = CALL; } break; \
+        case 32:  { constexpr int kN = 32;  rc = CALL; } break; \
+        case 64:  { constexpr int kN = 64;  rc = CALL; } break; \
+        case 128: { constexpr int kN = 128; rc = CALL; } break; \
+        case 256: { constexpr int kN = 256; rc = CALL; } break; \
+        default: rc = -1;                                       \
+    }
+
+// Resampling-operator tables the chain needs (device pointers on the GPU).
+struct ChainTables {
+    const int *mtx_rowptr, *mtx_colidx;        // CSR of mtx (M x M), rows = resampled bin
+    const float *mtx_vals_falloff;             // mtx[i][j] * falloff[j]      (forward K1)
+    const float *mtx_vals;                     // mtx[i][j]                   (backward K1)
+    const int *mtxi_rowptr, *mtxi_colidx;      // CSR of mtxi = mtx^T, rows = output bin
+    const float *mtxi_vals;                    // mtxi[j][i]                  (forward K5)
+    const float *mtxi_vals_falloff;            // mtxi[j][i] * falloff[j]     (backward K5)
+    const float2* filt;
+};
+
+// Runs the stages selected in `mask` (all five for a real call).
+//   forward : in = x (C,Tin,N,N) placed at [be, be+Tin);   out = y  (C,M,N,N)
+//   backward: in = gy (C,M,N,N) placed at [0, M);          out = gx (C,Tin,N,N) = rows [be, be+Tin)
+// `l.mark(i)` is called before stage i (i = 0..4) and once more (i = 5) at the end.
+template <class Launcher>
+int run_chain(Launcher& l, const ChainTables& t, int M, int N, int C, int D, int Tin,
+              int be_uniform, const int* be_dev, int c_base, const float* in, float* out,
+              float2* s1, float2* s2, bool backward, int mask = kStageAll) {
+    Params p{};
+    p.M = M; p.N = N; p.C = C; p.D = D;
+    p.s1 = s1; p.s2 = s2; p.filt = t.filt; p.conj_filter = backward ? 1 : 0;
+    p.in = in; p.out = out; p.c_base = c_base;
+    int rc = 0;
+    l.mark(0);
+    if (mask & kStageTimeFwd) {
+        p.in_T = backward ? M : Tin;
+        p.be_uniform = backward ? 0 : be_uniform;
+        p.be_dev = backward ? nullptr : be_dev;
+        p.rowptr = t.mtx_rowptr; p.colidx = t.mtx_colidx;
+        p.vals = backward ? t.mtx_vals : t.mtx_vals_falloff;
+        LCT_SWITCH_M(M, (launch_time_fwd<kM>(p, l)));
+        if (rc) return rc;
+    }
+    l.mark(1);
+    if (mask & kStageRowFwd) {
+        LCT_SWITCH_N(N, (launch_row_fwd<kN>(p, l)));
+        if (rc) return rc;
+    }
+    l.mark(2);
+    if (mask & kStageColFilter) {
+        LCT_SWITCH_N(N, (launch_col_filter<kN>(p, l)));
+        if (rc) return rc;
+    }
+    l.mark(3);
+    if (mask & kStageRowInv) {
+        LCT_SWITCH_N(N, (launch_row_inv<kN>(p, l)));
+        if (rc) return rc;
+    }
+    l.mark(4);
+    if (mask & kStageTimeInv) {
+        p.out_T = backward ? Tin : M;
+        p.be_uniform = backward ? be_uniform : 0;
+        p.be_dev = backward ? be_dev : nullptr;
+        p.rowptr = t.mtxi_rowptr; p.colidx = t.mtxi_colidx;
+        p.vals = backward ? t.mtxi_vals_falloff : t.mtxi_vals;
+        LCT_SWITCH_M(M, (launch_time_inv<kM>(p, l)));
+        if (rc) return rc;
+    }
+    l.mark(5);
+    return 0;
+}
+
+}  // namespace lct

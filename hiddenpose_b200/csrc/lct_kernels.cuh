@@ -1,0 +1,339 @@
+// The five LCT kernels (sm_100a), written as sequences of barrier-separated
+// phases so that the very same code can be stepped thread by thread on the CPU
+// by tests/emu (LCT_EMULATE; test infrastructure only, never a product path).
+//
+// Data flow for C = B*D channels, M time bins, N x N spatial grid
+// (reference: /root/reference/models/tflct.py:94-179):
+//
+//   K1 TimeFwd   x (C,Tin,N,N) f32 -> S1 (C,M+1,N,N) c64
+//                time window (tflct.py:104-110), falloff (:123-127), sqrt(t)
+//                resample as a CSR gather (:135-138), zero-extend to 2M (:140)
+//                and real FFT along T (first axis of :144), half spectrum.
+//   K2 RowFwd    S1 -> S2 (C,M+1,2N,N): zero-extended FFT along H (:144).
+//   K3 ColFilter S2 in place: zero-extended FFT along W, Wiener multiply
+//                (:145-150), inverse FFT along W, crop to N (:151,153).
+//   K4 RowInv    S2 -> S1 (C,M+1,N,N): inverse FFT along H, crop (:151,153).
+//   K5 TimeInv   S1 -> y (C,Tout,N,N) f32: Hermitian inverse FFT along T, crop
+//                to M, real part (:153), inverse resample mtxi as a CSR gather
+//                (:156-159) [+ falloff and window crop for the backward pass].
+//
+// The backward pass is the same chain with conj(filter), the falloff moved
+// from K1's input to K5's output and the window cut out at the end
+// (SURVEY.md section 3.5).
+#pragma once
+
+#include "lct_fft.cuh"
+
+namespace lct {
+
+#ifdef LCT_EMULATE
+extern float2 h_tw[kTwN];
+struct TwConst { static inline float2 get(int i) { return h_tw[i]; } };
+struct TwGlobal { static inline float2 get(int i) { return h_tw[i]; } };
+#define LCT_LDG(p) (*(p))
+#else
+__constant__ float2 c_tw[kTwN];          // exp(-2*pi*i*j/1024), built in double on the host
+__device__ float2 g_tw[kTwN];            // same table in global memory for lane-divergent lookups
+struct TwConst { static LCT_DEV float2 get(int i) { return c_tw[i]; } };
+struct TwGlobal { static LCT_DEV float2 get(int i) { return __ldg(&g_tw[i]); } };
+#define LCT_LDG(p) __ldg(p)
+#endif
+
+struct Params {
+    int M, N, C, D;
+    // K1 input placement: rows [in_be, in_be+in_T) of the M-bin time axis come from `in`
+    // (C, in_T, N*N); in_be is per batch sample when in_be_dev != nullptr.
+    // K5 output placement: rows [out_be, out_be+out_T) are written to `out` (C, out_T, N*N).
+    int in_T, out_T;
+    int be_uniform;
+    const int* be_dev;          // B entries or nullptr
+    int c_base;                 // global index of this launch's channel 0 (for be_dev lookups)
+    const float* in;
+    float* out;
+    float2* s1;                 // (C, M+1, N, N)
+    float2* s2;                 // (C, M+1, 2N, N)
+    const float2* filt;         // (M+1, 2N, 2N), already scaled by 1/(8 M N N)
+    int conj_filter;
+    // CSR of the resampling operator used by this launch (mtx rows for K1, mtxi rows for K5)
+    const int* rowptr;
+    const int* colidx;
+    const float* vals;
+};
+
+LCT_DEV int window_begin(const Params& p, int c) {
+    return p.be_dev ? LCT_LDG(p.be_dev + (p.c_base + c) / p.D) : p.be_uniform;
+}
+
+// ---------------------------------------------------------------------------
+// K1: time window + falloff + resample + real FFT (2M, M non-zero) along T.
+// Packed-real algorithm: z[n] = u[2n] + i u[2n+1] (n < M/2, zero above), Z = FFT_M(z),
+// X[k] = Ev + w^k Od with Ev = (Z[k] + conj Z[M-k])/2, Od = -i (Z[k] - conj Z[M-k])/2.
+// ---------------------------------------------------------------------------
+template <class P, int CT_> struct TimeFwd {
+    static constexpr int M = P::L, CT = CT_, kThreads = P::TL * CT;
+    static constexpr int kPhases = 3 + (P::S - 1) + 1;
+    static constexpr size_t kSmem = (size_t)M * CT * sizeof(float2);
+    struct Regs { float2 a[P::E]; };
+    static void grid(const Params& p, int& gx, int& gy) { gx = p.N * p.N / CT; gy = p.C; }
+    static int iterations(const Params&) { return 1; }
+
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs& r, unsigned char* smem, int tid, int bx, int by, int) {
+        const int col = tid % CT, tau = tid / CT;
+        const int NN = p.N * p.N, col0 = bx * CT, c = by;
+        float* xs = reinterpret_cast<float*>(smem);
+        float2* zs = reinterpret_cast<float2*>(smem);
+        if constexpr (PH == 0) {
+            const float* src = p.in + (size_t)c * p.in_T * NN + col0;
+            for (int i = tid; i < p.in_T * CT; i += kThreads) {
+                const int t = i / CT, cc = i % CT;
+                xs[i] = LCT_LDG(src + (size_t)t * NN + cc);
+            }
+        } else if constexpr (PH == 1) {
+            const int be = window_begin(p, c), en = be + p.in_T;
+            auto u_at = [&](int i) -> float {
+                float acc = 0.f;
+                const int e0 = LCT_LDG(p.rowptr + i), e1 = LCT_LDG(p.rowptr + i + 1);
+                for (int e = e0; e < e1; ++e) {
+                    const int j = LCT_LDG(p.colidx + e);
+                    if (j >= be && j < en) acc += LCT_LDG(p.vals + e) * xs[(j - be) * CT + col];
+                }
+                return acc;
+            };
+            fwd_stage<P, 0, true, TwConst>(tau,
+                [&](int pos, int) { return make_float2(u_at(2 * pos), u_at(2 * pos + 1)); },
+                [&](int, int slot, float2 v) { r.a[slot] = v; });
+        } else if constexpr (PH == 2) {
+            for_each_slot<P, 0>(tau, [&](int pos, int slot) { zs[pos * CT + col] = r.a[slot]; });
+        } else if constexpr (PH < 2 + P::S) {
+            constexpr int s = PH - 2;
+            fwd_stage<P, s, false, TwConst>(tau,
+                [&](int pos, int) { return zs[pos * CT + col]; },
+                [&](int pos, int, float2 v) { zs[pos * CT + col] = v; });
+        } else {
+            float2* dst = p.s1 + (size_t)c * (M + 1) * NN + col0 + col;
+            for (int k = tau; k <= M / 2; k += P::TL) {
+                const float2 zk = zs[P::freq_to_pos(k) * CT + col];
+                const float2 zm = cconj(zs[P::freq_to_pos((M - k) % M) * CT + col]);
+                const float2 ev = cscale(cadd(zk, zm), 0.5f);
+                const float2 d = csub(zk, zm);
+                const float2 od = make_float2(0.5f * d.y, -0.5f * d.x);
+                const float2 t = cmul(od, TwConst::get(k * (kTwN / (2 * M))));
+                dst[(size_t)k * NN] = cadd(ev, t);
+                if (k != M - k) dst[(size_t)(M - k) * NN] = cconj(csub(ev, t));
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// K5: Hermitian inverse FFT along T (keep t < M), real part, mtxi gather.
+// ---------------------------------------------------------------------------
+template <class P, int CT_> struct TimeInv {
+    static constexpr int M = P::L, CT = CT_, kThreads = P::TL * CT;
+    static constexpr int kPhases = 2 + P::S + 2;          // load | stage S-1 -> regs | scatter | middle.. | stage 0 -> regs | scatter vol | gather
+    static constexpr size_t kSmem = (size_t)(M + 1) * CT * sizeof(float2);
+    struct Regs { float2 a[P::E]; };
+    static void grid(const Params& p, int& gx, int& gy) { gx = p.N * p.N / CT; gy = p.C; }
+    static int iterations(const Params&) { return 1; }
+
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs& r, unsigned char* smem, int tid, int bx, int by, int) {
+        const int col = tid % CT, tau = tid / CT;
+        const int NN = p.N * p.N, col0 = bx * CT, c = by;
+        float2* zs = reinterpret_cast<float2*>(smem);
+        float* vol = reinterpret_cast<float*>(smem);
+        constexpr int SL = P::S - 1;
+        if constexpr (PH == 0) {
+            const float2* src = p.s1 + (size_t)c * (M + 1) * NN + col0;
+            for (int i = tid; i < (M + 1) * CT; i += kThreads) {
+                const int k = i / CT, cc = i % CT;
+                zs[i] = src[(size_t)k * NN + cc];
+            }
+        } else if constexpr (PH == 1) {
+            // Z[k] = (X[k] + conj X[M-k]) + i conj(w^k) (X[k] - conj X[M-k])
+            auto z_at = [&](int k) -> float2 {
+                const float2 xk = zs[k * CT + col];
+                const float2 xm = cconj(zs[(M - k) * CT + col]);
+                const float2 d = cmulc(csub(xk, xm), TwConst::get(k * (kTwN / (2 * M))));
+                return cadd(cadd(xk, xm), make_float2(-d.y, d.x));
+            };
+            if constexpr (SL == 0) {
+                inv_stage<P, 0, true, TwConst>(tau,
+                    [&](int pos, int) { return z_at(P::pos_to_freq(pos)); },
+                    [&](int, int slot, float2 v) { r.a[slot] = v; });
+            } else {
+                inv_stage<P, SL, false, TwConst>(tau,
+                    [&](int pos, int) { return z_at(P::pos_to_freq(pos)); },
+                    [&](int, int slot, float2 v) { r.a[slot] = v; });
+            }
+        } else if constexpr (PH == 2) {
+            if constexpr (SL == 0) {
+                for_each_slot_lower<P, 0>(tau, [&](int pos, int slot) {
+                    vol[(2 * pos) * CT + col] = r.a[slot].x;
+                    vol[(2 * pos + 1) * CT + col] = r.a[slot].y;
+                });
+            } else {
+                for_each_slot<P, SL>(tau, [&](int pos, int slot) { zs[pos * CT + col] = r.a[slot]; });
+            }
+        } else if constexpr (PH < 2 + SL) {          // middle stages SL-1 .. 1, in place
+            constexpr int s = SL - (PH - 2);
+            inv_stage<P, s, false, TwConst>(tau,
+                [&](int pos, int) { return zs[pos * CT + col]; },
+                [&](int pos, int, float2 v) { zs[pos * CT + col] = v; });
+        } else if constexpr (PH == 2 + SL && SL > 0) {
+            inv_stage<P, 0, true, TwConst>(tau,
+                [&](int pos, int) { return zs[pos * CT + col]; },
+                [&](int, int slot, float2 v) { r.a[slot] = v; });
+        } else if constexpr (PH == 3 + SL && SL > 0) {
+            for_each_slot_lower<P, 0>(tau, [&](int pos, int slot) {
+                vol[(2 * pos) * CT + col] = r.a[slot].x;
+                vol[(2 * pos + 1) * CT + col] = r.a[slot].y;
+            });
+        } else if constexpr (PH == kPhases - 1) {
+            const int be = window_begin(p, c);
+            float* dst = p.out + (size_t)c * p.out_T * NN + col0 + col;
+            for (int j = tau; j < p.out_T; j += P::TL) {
+                const int row = be + j;
+                float acc = 0.f;
+                const int e0 = LCT_LDG(p.rowptr + row), e1 = LCT_LDG(p.rowptr + row + 1);
+                for (int e = e0; e < e1; ++e) acc += LCT_LDG(p.vals + e) * vol[LCT_LDG(p.colidx + e) * CT + col];
+                dst[(size_t)j * NN] = acc;
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// K2: zero-extended forward FFT along H.  One block = one (c, kt) plane x CT columns.
+// ---------------------------------------------------------------------------
+template <class P, int CT_> struct RowFwd {
+    static constexpr int L = P::L, N = L / 2, CT = CT_, kThreads = P::TL * CT;
+    static constexpr int kPhases = P::S;
+    static constexpr size_t kSmem = (P::S > 1) ? (size_t)L * CT * sizeof(float2) : 0;
+    struct Regs {};
+    static void grid(const Params& p, int& gx, int& gy) { gx = p.N / CT; gy = p.C * (p.M + 1); }
+    static int iterations(const Params&) { return 1; }
+
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem, int tid, int bx, int by, int) {
+        const int col = tid % CT, tau = tid / CT;
+        float2* zs = reinterpret_cast<float2*>(smem);
+        const float2* src = p.s1 + (size_t)by * N * N + bx * CT + col;
+        float2* dst = p.s2 + (size_t)by * L * N + bx * CT + col;
+        auto ld_g = [&](int pos, int) { return src[(size_t)pos * N]; };
+        auto ld_s = [&](int pos, int) { return zs[pos * CT + col]; };
+        auto st_s = [&](int pos, int, float2 v) { zs[pos * CT + col] = v; };
+        auto st_g = [&](int pos, int, float2 v) { dst[(size_t)P::pos_to_freq(pos) * N] = v; };
+        if constexpr (P::S == 1) {
+            fwd_stage<P, 0, true, TwConst>(tau, ld_g, st_g);
+        } else if constexpr (PH == 0) {
+            fwd_stage<P, 0, true, TwConst>(tau, ld_g, st_s);
+        } else if constexpr (PH < P::S - 1) {
+            fwd_stage<P, PH, false, TwConst>(tau, ld_s, st_s);
+        } else {
+            fwd_stage<P, P::S - 1, false, TwConst>(tau, ld_s, st_g);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// K4: inverse FFT along H, keep h < N.
+// ---------------------------------------------------------------------------
+template <class P, int CT_> struct RowInv {
+    static constexpr int L = P::L, N = L / 2, CT = CT_, kThreads = P::TL * CT;
+    static constexpr int kPhases = P::S;
+    static constexpr size_t kSmem = (P::S > 1) ? (size_t)L * CT * sizeof(float2) : 0;
+    struct Regs {};
+    static void grid(const Params& p, int& gx, int& gy) { gx = p.N / CT; gy = p.C * (p.M + 1); }
+    static int iterations(const Params&) { return 1; }
+
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem, int tid, int bx, int by, int) {
+        const int col = tid % CT, tau = tid / CT;
+        float2* zs = reinterpret_cast<float2*>(smem);
+        const float2* src = p.s2 + (size_t)by * L * N + bx * CT + col;
+        float2* dst = p.s1 + (size_t)by * N * N + bx * CT + col;
+        auto ld_g = [&](int pos, int) { return src[(size_t)P::pos_to_freq(pos) * N]; };
+        auto ld_s = [&](int pos, int) { return zs[pos * CT + col]; };
+        auto st_s = [&](int pos, int, float2 v) { zs[pos * CT + col] = v; };
+        auto st_g = [&](int pos, int, float2 v) { dst[(size_t)pos * N] = v; };
+        if constexpr (P::S == 1) {
+            inv_stage<P, 0, true, TwConst>(tau, ld_g, st_g);
+        } else if constexpr (PH == 0) {
+            inv_stage<P, P::S - 1, false, TwConst>(tau, ld_g, st_s);
+        } else if constexpr (PH < P::S - 1) {
+            inv_stage<P, P::S - 1 - PH, false, TwConst>(tau, ld_s, st_s);
+        } else {
+            inv_stage<P, 0, true, TwConst>(tau, ld_s, st_g);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// K3: along W (the contiguous axis): zero-extended FFT, filter multiply, inverse
+// FFT, crop -- in place on S2.  One block = RB consecutive kh rows of one kt
+// plane; it loops over the channels so the filter row stays in registers.
+// Two-stage plans only (lanes run along the line so global accesses coalesce).
+// ---------------------------------------------------------------------------
+template <class P, int RB_> struct ColFilter {
+    static_assert(P::S == 2, "ColFilter needs a two-stage plan");
+    static constexpr int L = P::L, N = L / 2, RB = RB_, kThreads = P::TL * RB;
+    static constexpr int kPhases = 3;
+    static constexpr int PAD = 1;
+    static constexpr int RS = L + P::R0 * PAD + ((P::TL < 16) ? 8 : 0);    // row stride in float2
+    static constexpr size_t kSmem = (size_t)RB * RS * sizeof(float2);
+    struct Regs { float2 w[P::E]; };
+    static void grid(const Params& p, int& gx, int& gy) { gx = L / RB; gy = p.M + 1; }
+    static int iterations(const Params& p) { return p.C; }
+    static LCT_DEV int padpos(int pos) { return pos + (pos / P::st(0)) * PAD; }
+
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs& r, unsigned char* smem, int tid, int bx, int by, int it) {
+        const int tau = tid % P::TL, rl = tid / P::TL;
+        const int kh = bx * RB + rl, kt = by, c = it;
+        float2* zs = reinterpret_cast<float2*>(smem) + rl * RS;
+        float2* row = p.s2 + (((size_t)c * (p.M + 1) + kt) * L + kh) * N;
+        if constexpr (PH == 0) {
+            if (it == 0) {
+                const float2* f = p.filt + ((size_t)kt * L + kh) * L;
+                for_each_slot<P, 1>(tau, [&](int pos, int slot) {
+                    float2 w = LCT_LDG(f + P::pos_to_freq(pos));
+                    if (p.conj_filter) w.y = -w.y;
+                    r.w[slot] = w;
+                });
+            }
+            fwd_stage<P, 0, true, TwGlobal>(tau,
+                [&](int pos, int) { return row[pos]; },
+                [&](int pos, int, float2 v) { zs[padpos(pos)] = v; });
+        } else if constexpr (PH == 1) {
+            float2 a[P::E];
+            fwd_stage<P, 1, false, TwGlobal>(tau,
+                [&](int pos, int) { return zs[padpos(pos)]; },
+                [&](int, int slot, float2 v) { a[slot] = cmul(v, r.w[slot]); });
+            inv_stage<P, 1, false, TwGlobal>(tau,
+                [&](int, int slot) { return a[slot]; },
+                [&](int pos, int, float2 v) { zs[padpos(pos)] = v; });
+        } else {
+            inv_stage<P, 0, true, TwGlobal>(tau,
+                [&](int pos, int) { return zs[padpos(pos)]; },
+                [&](int pos, int, float2 v) { row[pos] = v; });
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// generic kernel driver
+// ---------------------------------------------------------------------------
+#ifndef LCT_EMULATE
+template <class K, int PH> struct PhaseLoop {
+    static LCT_DEV void run(const Params& p, typename K::Regs& r, unsigned char* smem, int it) {
+        K::template phase<PH>(p, r, smem, threadIdx.x, blockIdx.x, blockIdx.y, it);
+        __syncthreads();
+        if constexpr (PH + 1 < K::kPhases) PhaseLoop<K, PH + 1>::run(p, r, smem, it);
+    }
+};
+
+template <class K> __global__ void __launch_bounds__(K::kThreads) lct_kernel(const Params p, const int iters) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    typename K::Regs r;
+    for (int it = 0; it < iters; ++it) PhaseLoop<K, 0>::run(p, r, smem, it);
+}
+#endif
+
+}  // namespace lct

@@ -1,0 +1,78 @@
+"""Drop-in for /root/reference/models/feature_propagation.py: ``FeaturePropagation``,
+``LCT``, ``normalize``, ``normalize_feature`` and ``VisibleNet`` -- the names
+models/NlosPose.py:7 imports."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .layer import LctLayerBase
+
+
+class LCT(LctLayerBase):
+    """``LCT(image_size, time_size, bin_len, wall_size, mode, material)`` -- feature_propagation.py:48-69."""
+
+    def __init__(self, image_size=256, time_size=128, bin_len=0.01, wall_size=2.0, mode="lct", material="diffuse"):
+        super().__init__()
+        self.image_size = image_size
+        self.time_size = time_size
+        assert 2 ** int(np.log2(self.time_size)) == time_size, \
+            "time size should be a power of 2"                       # feature_propagation.py:61-62
+        self.bin_len = bin_len
+        self.wall_size = wall_size
+        self.mode = mode
+        self.material = material
+        self._parpareparam()
+
+    def _parpareparam(self):
+        self._setup(self.image_size, self.time_size, self.bin_len, self.wall_size, self.mode, self.material)
+        # the reference ends with todev('cuda', 1) (feature_propagation.py:109); FeaturePropagation
+        # immediately overrides it with its own (dev, dnum), so the plan is created there.
+
+
+class FeaturePropagation(nn.Module):
+    """feature_propagation.py:18-44.
+    Input : Tensor (batch_size, channels, time_size, image_size[0], image_size[1])
+    Output: Tensor (batch_size, channels, time_size, image_size[0], image_size[1])
+    """
+
+    def __init__(self, image_size=256, time_size=512, bin_len=0.01, wall_size=2.0, mode="lct",
+                 material="diffuse", dnum=1, dev="cpu"):
+        super().__init__()
+        assert mode == "lct", f"{mode} is not spported. Feature propagation only support lct by now"
+        self.method = LCT(int(image_size), time_size, bin_len, wall_size, mode=mode, material=material)
+        self.method.todev(dev, dnum)
+
+    def forward(self, x, time_begin, time_end):
+        return self.method(x, time_begin, time_end)
+
+
+def normalize(data_bxcxdxhxw):
+    """feature_propagation.py:260-270: per (b, c) min/max normalisation to [0, 1]."""
+    b, c, d, h, w = data_bxcxdxhxw.shape
+    flat = data_bxcxdxhxw.reshape(b, c, -1)
+    shifted = flat - flat.min(2, keepdim=True)[0]
+    return (shifted / (shifted.max(2, keepdim=True)[0] + 1e-15)).view(b, c, d, h, w)
+
+
+def normalize_feature(data_bxcxdxhxw):
+    """feature_propagation.py:273-286: min/max normalisation times 10.
+
+    The reference calls ``nn.ReLU()(x)`` and discards the result (line 274), so
+    negative LCT values do reach the ``min``; that behaviour is kept.
+    """
+    return normalize(data_bxcxdxhxw) * 10.0
+
+
+class VisibleNet(nn.Module):
+    """feature_propagation.py:289-312 (only used by the 2-D backbone)."""
+
+    def __init__(self, basedim, layernum=0):
+        super().__init__()
+        self.layernum = layernum
+
+    def forward(self, x):
+        x = normalize(torch.relu(x)) * 1.0e5
+        depdim = x.shape[2]
+        val, dep = x.topk(4, dim=2)
+        dep = (depdim - 1 - dep.float()) / (depdim - 1)
+        return torch.cat([val, dep], dim=1)

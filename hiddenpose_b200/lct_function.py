@@ -1,0 +1,140 @@
+"""Device plan + autograd.Function over the C ABI (include/hiddenpose_lct.h).
+
+Replaces the body of /root/reference/models/tflct.py:94-179 and the backward
+autograd derives from it.  The layer is a fixed linear operator, so nothing is
+saved for backward except the integer window.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native
+
+
+def _i32_array(values):
+    arr = (ctypes.c_int32 * len(values))(*[int(v) for v in values])
+    return arr
+
+
+class LctPlan:
+    """Owns one ``lct_plan*`` (immutable device constants) on one CUDA device."""
+
+    def __init__(self, M, N, csr, falloff, filter_half, device, lapw=None, workspace_limit_bytes=16 << 30):
+        if device.type != "cuda":
+            raise RuntimeError("LctPlan needs a CUDA device; there is no CPU implementation of this layer")
+        self.lib = _native.load()
+        self.M, self.N, self.device = int(M), int(N), device
+        self.lapw = None if lapw is None else np.ascontiguousarray(lapw, dtype=np.float32).ravel()
+        self.workspace_limit_bytes = int(workspace_limit_bytes)
+        rowptr = np.ascontiguousarray(csr[0], dtype=np.int32)
+        colidx = np.ascontiguousarray(csr[1], dtype=np.int32)
+        vals = np.ascontiguousarray(csr[2], dtype=np.float32)
+        filt = np.ascontiguousarray(filter_half, dtype=np.complex64)
+        if filt.shape != (M + 1, 2 * N, 2 * N):
+            raise ValueError(f"filter_half must be {(M + 1, 2 * N, 2 * N)}, got {filt.shape}")
+        fall = None if falloff is None else np.ascontiguousarray(falloff, dtype=np.float32)
+        f32p, i32p = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
+        desc = _native.LctDesc(
+            time_bins=M, spatial=N, device=device.index if device.index is not None else torch.cuda.current_device(),
+            reserved=0, mtx_rowptr=rowptr.ctypes.data_as(i32p), mtx_colidx=colidx.ctypes.data_as(i32p),
+            mtx_vals=vals.ctypes.data_as(f32p), falloff=None if fall is None else fall.ctypes.data_as(f32p),
+            filter_half=filt.view(np.float32).ctypes.data_as(f32p))
+        handle = ctypes.c_void_p()
+        _native.check(self.lib.lct_plan_create(ctypes.byref(desc), ctypes.byref(handle)))
+        del rowptr, colidx, vals, fall, filt      # host tables were copied to the device
+        self.handle = handle
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                self.lib.lct_plan_destroy(h)
+            except Exception:
+                pass
+
+    # ------------------------------------------------------------------
+    def workspace(self, channels):
+        per = self.lib.lct_plan_workspace_bytes(self.handle, 1)
+        head = 2 * per - self.lib.lct_plan_workspace_bytes(self.handle, 2)       # fixed header
+        per_channel = per - head
+        fit = max(1, (self.workspace_limit_bytes - head) // per_channel)
+        nbytes = head + per_channel * min(int(channels), int(fit))
+        return torch.empty(nbytes, dtype=torch.uint8, device=self.device), nbytes
+
+    def _run(self, fn, src, tbes, tens, B, D, Tin, dst):
+        ws, nbytes = self.workspace(B * D)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _native.check(fn(self.handle, src.data_ptr(), _i32_array(tbes), _i32_array(tens), B, D, Tin,
+                         dst.data_ptr(), ws.data_ptr(), nbytes, stream))
+
+    def forward(self, x, tbes, tens):
+        B, D, Tin, H, W = x.shape
+        y = torch.empty((B, D, self.M, H, W), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(self.device):
+            self._run(self.lib.lct_forward, x, tbes, tens, B, D, Tin, y)
+        return y
+
+    def backward(self, gy, tbes, tens, Tin):
+        B, D, M, H, W = gy.shape
+        gx = torch.empty((B, D, Tin, H, W), dtype=torch.float32, device=gy.device)
+        with torch.cuda.device(self.device):
+            self._run(self.lib.lct_backward, gy, tbes, tens, B, D, Tin, gx)
+        return gx
+
+    def run_staged(self, src, tbes, tens, Tin, events, backward=False):
+        """Measurement hook (lct_run_staged): forward or backward with six torch CUDA events
+        recorded around the five kernels.  Returns the output tensor."""
+        B, D = src.shape[0], src.shape[1]
+        out_t = Tin if backward else self.M
+        dst = torch.empty((B, D, out_t, self.N, self.N), dtype=torch.float32, device=src.device)
+        ws, nbytes = self.workspace(B * D)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        handles = (ctypes.c_void_p * 6)(*[ctypes.c_void_p(e.cuda_event) for e in events])
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.lct_run_staged(self.handle, src.data_ptr(), _i32_array(tbes), _i32_array(tens),
+                                                  B, D, Tin, dst.data_ptr(), ws.data_ptr(), nbytes, stream,
+                                                  1 if backward else 0, handles))
+        return dst
+
+    def laplacian(self, vol, adjoint):
+        out = torch.empty_like(vol)
+        C = vol.shape[0] * vol.shape[1]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.lct_bp_laplacian(
+                self.handle, vol.data_ptr(), out.data_ptr(), C,
+                self.lapw.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), 1 if adjoint else 0, stream))
+        return out
+
+    def forward_host(self, x_host, tbes, tens):
+        """Host-buffer entry point (lct_forward_host): H2D, forward, D2H, sync."""
+        B, D, Tin, H, W = x_host.shape
+        y_host = torch.empty((B, D, self.M, H, W), dtype=torch.float32, pin_memory=x_host.is_pinned())
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.lct_forward_host(self.handle, x_host.data_ptr(), _i32_array(tbes), _i32_array(tens),
+                                                    B, D, Tin, y_host.data_ptr(), stream))
+        return y_host
+
+
+class LctFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, plan, tbes, tens):
+        ctx.plan, ctx.tbes, ctx.tens, ctx.tin = plan, tuple(tbes), tuple(tens), x.shape[2]
+        y = plan.forward(x, tbes, tens)
+        if plan.lapw is not None:                       # method == 'bp' (tflct.py:164-175)
+            y = plan.laplacian(y, adjoint=False)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None
+        plan = ctx.plan
+        gy = gy.contiguous().float()
+        if plan.lapw is not None:
+            gy = plan.laplacian(gy, adjoint=True)
+        return plan.backward(gy, ctx.tbes, ctx.tens, ctx.tin), None, None, None

@@ -1,0 +1,124 @@
+/*
+ * hiddenpose_lct.h -- C ABI of the B200 (sm_100a) light-cone-transform library.
+ *
+ * Drop-in boundary for the LCT layer of Hagtaril/HiddenPose.  The reference has
+ * no FFI: its layer is a Python nn.Module over PyTorch library calls.  Each entry
+ * point below names the piece of the reference it replaces:
+ *
+ *   lct_plan_create    <- lct.parpareparam + lct.todev      models/tflct.py:32-92
+ *                         (== LCT._parpareparam + LCT.todev models/feature_propagation.py:71-109,173-184)
+ *                         operators come from              utils/helper.py:35-69,72-125
+ *   lct_forward        <- lct.forward                       models/tflct.py:94-179
+ *                         (== LCT.forward                   models/feature_propagation.py:186-257)
+ *   lct_backward       <- the autograd-derived backward of that forward (the reference has no
+ *                         explicit backward; it is the adjoint of the same linear chain,
+ *                         SURVEY.md section 3.5)
+ *   lct_bp_laplacian   <- the method=='bp' tail             models/tflct.py:164-175
+ *
+ * Plain C types only: pointers, sizes, integer return codes (0 = success).  Nothing
+ * throws across this boundary.  Device pointers are raw CUDA device addresses; `stream`
+ * is a cudaStream_t passed as void*.  The caller owns all data buffers and the
+ * workspace; a plan owns only immutable device constants, so one plan may be shared by
+ * threads and streams as long as concurrent calls use distinct workspaces.
+ * Calls are asynchronous on `stream`; they never allocate or synchronise
+ * (lct_forward_host is the exception and says so).
+ */
+#ifndef HIDDENPOSE_LCT_H_
+#define HIDDENPOSE_LCT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCT_OK 0
+#define LCT_ERR_INVALID 1      /* bad argument (shape, window, null pointer) */
+#define LCT_ERR_UNSUPPORTED 2  /* M or N outside the compiled set */
+#define LCT_ERR_CUDA 3         /* a CUDA runtime call failed; see lct_last_error() */
+#define LCT_ERR_WORKSPACE 4    /* workspace smaller than lct_plan_workspace_bytes(plan, 1) */
+#define LCT_ERR_NOMEM 5
+
+#define LCT_ABI_VERSION 1
+
+typedef struct lct_plan lct_plan;
+
+/* Operators, all in HOST memory, copied to the device by lct_plan_create. */
+typedef struct lct_desc {
+    int32_t time_bins;          /* M: `crop` / `time_size`; power of two in [32, 512]            */
+    int32_t spatial;            /* N: `spatial` / `image_size` (H == W); power of two in [8, 256] */
+    int32_t device;             /* CUDA device ordinal                                            */
+    int32_t reserved;           /* must be 0                                                      */
+    const int32_t* mtx_rowptr;  /* M+1   CSR row pointers of mtx (helper.py:35-69)                */
+    const int32_t* mtx_colidx;  /* nnz                                                            */
+    const float* mtx_vals;      /* nnz                                                            */
+    const float* falloff;       /* M     gridz**4 | **2 (tflct.py:123-127); NULL = no falloff     */
+    const float* filter_half;   /* (M+1, 2N, 2N, 2) interleaved re/im: planes kt = 0..M of invpsf
+                                   (tflct.py:57-65), unscaled                                     */
+} lct_desc;
+
+int lct_abi_version(void);
+const char* lct_error_string(int code);
+/* Detail of the last failure on the calling thread ("" if none). */
+const char* lct_last_error(void);
+
+int lct_plan_create(const lct_desc* desc, lct_plan** out);
+void lct_plan_destroy(lct_plan* plan);
+int32_t lct_plan_time_bins(const lct_plan* plan);
+int32_t lct_plan_spatial(const lct_plan* plan);
+
+/* Bytes of device scratch that let `channels` (= B*D) volumes run as one batch.  Any
+ * workspace >= lct_plan_workspace_bytes(plan, 1) is accepted; smaller-than-full
+ * workspaces make the call process the channels in several batches. */
+size_t lct_plan_workspace_bytes(const lct_plan* plan, int32_t channels);
+
+/*
+ * y[b,d,:,:,:] = LCT(x[b,d,:,:,:]) with x placed at time bins [tbe[b], ten[b]).
+ *   x   device, float32, (B, D, Tin, N, N) contiguous
+ *   y   device, float32, (B, D, M,   N, N) contiguous
+ *   tbe, ten  HOST arrays of B int32; 0 <= tbe[b], ten[b] <= M, ten[b]-tbe[b] == Tin
+ */
+int lct_forward(const lct_plan* plan, const float* x, const int32_t* tbe, const int32_t* ten,
+                int32_t B, int32_t D, int32_t Tin, float* y,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * gx = (d LCT / d x)^T gy : gradient w.r.t. x of sum(y * gy).
+ *   gy  device, float32, (B, D, M,   N, N);   gx  device, float32, (B, D, Tin, N, N)
+ */
+int lct_backward(const lct_plan* plan, const float* gy, const int32_t* tbe, const int32_t* ten,
+                 int32_t B, int32_t D, int32_t Tin, float* gx,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Measurement hook: lct_forward (backward == 0) or lct_backward (backward != 0) with six
+ * caller-created cudaEvent_t recorded on `stream`: events6[i] before kernel i (time-forward,
+ * row-forward, column-filter, row-inverse, time-inverse) and events6[5] after the last one.
+ * Needs a workspace for the whole batch.  Same results as the plain calls.
+ */
+int lct_run_staged(const lct_plan* plan, const float* in, const int32_t* tbe, const int32_t* ten,
+                   int32_t B, int32_t D, int32_t Tin, float* out,
+                   void* workspace, size_t workspace_bytes, void* stream,
+                   int32_t backward, void* const* events6);
+
+/*
+ * method=='bp' tail (tflct.py:164-175): out = conv3d(replicate_pad(vol, 2), lapw 5x5x5),
+ * then out[:, 0] = 0.  `adjoint` != 0 applies the transpose (for the backward pass).
+ *   vol, out  device, float32, (C, M, N, N), must not alias;  lapw  HOST, 125 floats.
+ */
+int lct_bp_laplacian(const lct_plan* plan, const float* vol, float* out, int32_t channels,
+                     const float* lapw, int32_t adjoint, void* stream);
+
+/*
+ * Host-buffer convenience: copies x from host memory, runs lct_forward, copies y back and
+ * SYNCHRONISES `stream`.  Allocates its device scratch from the stream-ordered allocator.
+ * Pinned host buffers make the copies asynchronous to each other.
+ */
+int lct_forward_host(const lct_plan* plan, const float* x_host, const int32_t* tbe, const int32_t* ten,
+                     int32_t B, int32_t D, int32_t Tin, float* y_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIDDENPOSE_LCT_H_ */

@@ -150,7 +150,7 @@ class LctOracle:
     # ----------------------------------------------------------------------
     def forward(self, feat, tbes, tens):
         """tflct.py:94-179, op for op, in ``self.dtype`` on the CPU."""
-        dt = self.dtype
+        dt, dev = self.dtype, feat.device      # dev is the CPU everywhere except the large-size GPU cross-checks in tests/
         feat = feat.to(dt)
         bnum, dnum, tnum, hnum, wnum = feat.shape
         M, N = self.crop, self.spatial_grid
@@ -159,37 +159,37 @@ class LctOracle:
             assert ten <= M
         padded = []
         for i in range(bnum):                               # tflct.py:104-110
-            head = torch.zeros((1, dnum, tbes[i], hnum, wnum), dtype=dt)
-            tail = torch.zeros((1, dnum, M - tens[i], hnum, wnum), dtype=dt)
+            head = torch.zeros((1, dnum, tbes[i], hnum, wnum), dtype=dt, device=dev)
+            tail = torch.zeros((1, dnum, M - tens[i], hnum, wnum), dtype=dt, device=dev)
             padded.append(torch.cat([head, feat[i:i + 1], tail], dim=2))
         data = torch.cat(padded, dim=0)
         assert hnum == wnum and hnum == N                   # tflct.py:113-114
         data = data.view(bnum * dnum, M, hnum, wnum)        # tflct.py:121
 
-        gridz = self.gridz.to(dt)
+        gridz = self.gridz.to(dev, dt)
         if self.material == "diffuse":                      # tflct.py:124-127
             data = data * (gridz ** 4)
         elif self.material == "specular":
             data = data * (gridz ** 2)
 
-        pad = torch.zeros((bnum * dnum, 2 * M, 2 * N, 2 * N), dtype=dt)        # tflct.py:131-133
-        tmp = torch.matmul(self.mtx.to(dt), data.view(bnum * dnum, M, -1))     # tflct.py:135-138
+        pad = torch.zeros((bnum * dnum, 2 * M, 2 * N, 2 * N), dtype=dt, device=dev)        # tflct.py:131-133
+        tmp = torch.matmul(self.mtx.to(dev, dt), data.view(bnum * dnum, M, -1))     # tflct.py:135-138
         pad[:, :M, :N, :N] = tmp.view(bnum * dnum, M, N, N)                    # tflct.py:140
 
         fre = torch.fft.fftn(pad, dim=(-3, -2, -1))                            # tflct.py:144
         fr, fi = fre.real, fre.imag
-        wr, wi = self.invpsf_real.to(dt), self.invpsf_imag.to(dt)
+        wr, wi = self.invpsf_real.to(dev, dt), self.invpsf_imag.to(dev, dt)
         re_real = fr * wr - fi * wi                                            # tflct.py:148
         re_imag = fr * wi + fi * wr                                            # tflct.py:149
         re = torch.fft.ifftn(torch.complex(re_real, re_imag), dim=(-3, -2, -1))  # tflct.py:150-151
 
         vol = re.real[:, :M, :N, :N]                                           # tflct.py:153
-        out = torch.matmul(self.mtxi.to(dt), vol.reshape(bnum * dnum, M, -1))  # tflct.py:156-159
+        out = torch.matmul(self.mtxi.to(dev, dt), vol.reshape(bnum * dnum, M, -1))  # tflct.py:156-159
         out = out.view(bnum * dnum, M, N, N)
 
         if self.method == "bp":                                                # tflct.py:164-175
             v = torch.nn.functional.pad(out.unsqueeze(1), (2,) * 6, mode="replicate")
-            v = torch.nn.functional.conv3d(v, self.lapw.to(dt))
+            v = torch.nn.functional.conv3d(v, self.lapw.to(dev, dt))
             out = v.squeeze(1)
             out[:, :1] = 0
         return out.view(bnum, dnum, M, hnum, wnum)                             # tflct.py:177-179
@@ -200,7 +200,7 @@ class LctOracle:
         """Gradient of ``sum(forward(x) * grad_out)`` w.r.t. x, by autograd
         through :meth:`forward` -- what the reference's backward computes
         (the reference has no explicit backward)."""
-        x = torch.zeros(feat_shape, dtype=self.dtype, requires_grad=True)
+        x = torch.zeros(feat_shape, dtype=self.dtype, device=grad_out.device, requires_grad=True)
         y = self.forward(x, tbes, tens)
         (g,) = torch.autograd.grad(y, x, grad_out.to(self.dtype))
         return g

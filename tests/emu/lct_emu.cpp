@@ -1,0 +1,79 @@
+// CPU thread emulator for the LCT kernels -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles hiddenpose_b200/csrc/lct_kernels.cuh with LCT_EMULATE and steps every
+// block phase by phase, thread by thread, with the same index math the GPU runs.
+// It exists because the build container has no GPU: kernel logic is debugged here,
+// then confirmed on a B200.  It is never loaded by the hiddenpose_b200 package.
+#define LCT_EMULATE 1
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "lct_chain.cuh"
+
+namespace lct {
+float2 h_tw[kTwN];
+}
+
+namespace {
+
+bool g_reverse_threads = false;   // run threads in reverse order inside a phase: exposes intra-phase races
+
+template <class K, int PH> struct EmuPhases {
+    static void run(const lct::Params& p, std::vector<typename K::Regs>& regs, unsigned char* smem, int bx, int by, int it) {
+        if (!g_reverse_threads)
+            for (int tid = 0; tid < K::kThreads; ++tid) K::template phase<PH>(p, regs[tid], smem, tid, bx, by, it);
+        else
+            for (int tid = K::kThreads - 1; tid >= 0; --tid) K::template phase<PH>(p, regs[tid], smem, tid, bx, by, it);
+        if constexpr (PH + 1 < K::kPhases) EmuPhases<K, PH + 1>::run(p, regs, smem, bx, by, it);
+    }
+};
+
+struct EmuLauncher {
+    void mark(int) {}
+    template <class K> int launch(const lct::Params& p) {
+        int gx, gy;
+        K::grid(p, gx, gy);
+        const int iters = K::iterations(p);
+        std::vector<unsigned char> smem(K::kSmem + 64);
+        std::vector<typename K::Regs> regs(K::kThreads);
+        for (int by = 0; by < gy; ++by)
+            for (int bx = 0; bx < gx; ++bx) {
+                // poison shared memory so reads of never-written slots surface as NaN
+                float* f = reinterpret_cast<float*>(smem.data());
+                for (size_t i = 0; i < smem.size() / 4; ++i) f[i] = std::numeric_limits<float>::quiet_NaN();
+                for (int it = 0; it < iters; ++it) EmuPhases<K, 0>::run(p, regs, smem.data(), bx, by, it);
+            }
+        return 0;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+void lct_emu_init(int reverse_threads) {
+    g_reverse_threads = reverse_threads != 0;
+    for (int j = 0; j < lct::kTwN; ++j) {
+        const double a = -2.0 * M_PI * j / lct::kTwN;
+        lct::h_tw[j].x = (float)std::cos(a);
+        lct::h_tw[j].y = (float)std::sin(a);
+    }
+}
+
+// All pointers are host pointers.  `filt` must already carry the 1/(8 M N N) scale.
+int lct_emu_run(int M, int N, int C, int D, int Tin, int be_uniform, const int* be,
+                const float* in, float* out, float* s1, float* s2,
+                const int* mtx_rowptr, const int* mtx_colidx, const float* mtx_vals_falloff, const float* mtx_vals,
+                const int* mtxi_rowptr, const int* mtxi_colidx, const float* mtxi_vals, const float* mtxi_vals_falloff,
+                const float* filt, int backward, int mask) {
+    lct::ChainTables t{mtx_rowptr, mtx_colidx, mtx_vals_falloff, mtx_vals,
+                       mtxi_rowptr, mtxi_colidx, mtxi_vals, mtxi_vals_falloff,
+                       reinterpret_cast<const float2*>(filt)};
+    EmuLauncher l;
+    return lct::run_chain(l, t, M, N, C, D, Tin, be_uniform, be, 0, in, out,
+                          reinterpret_cast<float2*>(s1), reinterpret_cast<float2*>(s2), backward != 0, mask);
+}
+
+}  // extern "C"

