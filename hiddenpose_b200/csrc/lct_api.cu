@@ -13,6 +13,7 @@
 #include "hiddenpose_lct.h"
 #include "lct_chain.cuh"
 #include "lct_stencil.cuh"
+#include "lct_tables.h"
 
 namespace {
 
@@ -79,8 +80,13 @@ struct GpuLauncher {
     template <class K> int launch(const lct::Params& p) {
         static bool attr_set[kMaxDevices] = {};
         auto kern = lct::lct_kernel<K>;
-        if (K::kSmem > 48 * 1024 && !attr_set[device]) {
-            err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::kSmem);
+        if (!attr_set[device]) {
+            if (K::kSmem > 48 * 1024) {
+                err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::kSmem);
+                if (err != cudaSuccess) return 1;
+            }
+            // ask for the full shared-memory carve-out so occupancy is not capped at one block's worth
+            err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (err != cudaSuccess) return 1;
             attr_set[device] = true;
         }
@@ -107,17 +113,35 @@ __global__ void scale_filter_kernel(float2* f, size_t n, float s) {
 
 }  // namespace
 
+struct DeviceBand {
+    float4* ell = nullptr;
+    int* rowptr = nullptr;
+    float* vals = nullptr;
+    lct::BandTable view() const { return lct::BandTable{ell, rowptr, vals}; }
+    void release() { cudaFree(ell); cudaFree(rowptr); cudaFree(vals); ell = nullptr; rowptr = nullptr; vals = nullptr; }
+};
+
 struct lct_plan {
     int M = 0, N = 0, device = 0;
-    int *mtx_rowptr = nullptr, *mtx_colidx = nullptr, *mtxi_rowptr = nullptr, *mtxi_colidx = nullptr;
-    float *mtx_vals = nullptr, *mtx_vals_falloff = nullptr, *mtxi_vals = nullptr, *mtxi_vals_falloff = nullptr;
+    DeviceBand mtx_falloff, mtx, mtxi, mtxi_falloff;
     float2* filt = nullptr;
     size_t per_channel_bytes() const { return (size_t)(M + 1) * N * N * sizeof(float2) * 3; }
     lct::ChainTables tables() const {
-        return lct::ChainTables{mtx_rowptr, mtx_colidx, mtx_vals_falloff, mtx_vals,
-                                mtxi_rowptr, mtxi_colidx, mtxi_vals, mtxi_vals_falloff, filt};
+        return lct::ChainTables{mtx_falloff.view(), mtx.view(), mtxi.view(), mtxi_falloff.view(), filt};
     }
 };
+
+namespace {
+int upload_band(const std::vector<lct::EllRow>& ell, const std::vector<int32_t>& rowptr, const std::vector<float>& vals,
+                DeviceBand& out) {
+    static_assert(sizeof(lct::EllRow) == sizeof(float4), "EllRow must be 16 bytes");
+    int rc = to_device(reinterpret_cast<const float4*>(ell.data()), ell.size(), &out.ell);
+    if (rc) return rc;
+    rc = to_device(rowptr.data(), rowptr.size(), &out.rowptr);
+    if (rc) return rc;
+    return to_device(vals.data(), vals.size(), &out.vals);
+}
+}  // namespace
 
 extern "C" {
 
@@ -140,8 +164,7 @@ const char* lct_last_error(void) { return g_last_error.c_str(); }
 void lct_plan_destroy(lct_plan* plan) {
     if (!plan) return;
     DeviceGuard g(plan->device);
-    cudaFree(plan->mtx_rowptr); cudaFree(plan->mtx_colidx); cudaFree(plan->mtxi_rowptr); cudaFree(plan->mtxi_colidx);
-    cudaFree(plan->mtx_vals); cudaFree(plan->mtx_vals_falloff); cudaFree(plan->mtxi_vals); cudaFree(plan->mtxi_vals_falloff);
+    plan->mtx_falloff.release(); plan->mtx.release(); plan->mtxi.release(); plan->mtxi_falloff.release();
     cudaFree(plan->filt);
     delete plan;
 }
@@ -158,47 +181,20 @@ int lct_plan_create(const lct_desc* d, lct_plan** out) {
     int rc = upload_twiddles(d->device);
     if (rc) return rc;
 
-    // validate the CSR and build its transpose (mtxi = mtx^T, helper.py:61) on the host
-    const int nnz = d->mtx_rowptr[M];
-    if (d->mtx_rowptr[0] != 0 || nnz <= 0) return fail(LCT_ERR_INVALID, "bad CSR row pointers");
-    for (int i = 0; i < M; ++i)
-        if (d->mtx_rowptr[i + 1] < d->mtx_rowptr[i]) return fail(LCT_ERR_INVALID, "CSR row pointers not monotone");
-    for (int e = 0; e < nnz; ++e)
-        if (d->mtx_colidx[e] < 0 || d->mtx_colidx[e] >= M) return fail(LCT_ERR_INVALID, "CSR column index out of range");
-    std::vector<float> fall(M, 1.0f);
-    if (d->falloff) std::memcpy(fall.data(), d->falloff, sizeof(float) * M);
-    std::vector<float> vals_f(nnz);
-    std::vector<int> t_rowptr(M + 1, 0), t_colidx(nnz);
-    std::vector<float> t_vals(nnz), t_vals_f(nnz);
-    for (int e = 0; e < nnz; ++e) {
-        vals_f[e] = d->mtx_vals[e] * fall[d->mtx_colidx[e]];
-        t_rowptr[d->mtx_colidx[e] + 1]++;
-    }
-    for (int j = 0; j < M; ++j) t_rowptr[j + 1] += t_rowptr[j];
-    {
-        std::vector<int> cursor(t_rowptr.begin(), t_rowptr.end() - 1);
-        for (int i = 0; i < M; ++i)
-            for (int e = d->mtx_rowptr[i]; e < d->mtx_rowptr[i + 1]; ++e) {
-                const int j = d->mtx_colidx[e], dst = cursor[j]++;
-                t_colidx[dst] = i;
-                t_vals[dst] = d->mtx_vals[e];
-                t_vals_f[dst] = d->mtx_vals[e] * fall[j];
-            }
-    }
+    // validate the operator and derive the banded row tables for mtx and mtxi = mtx^T (helper.py:61)
+    lct::HostTables ht;
+    const std::string why = lct::build_tables(M, d->mtx_rowptr, d->mtx_colidx, d->mtx_vals, d->falloff, ht);
+    if (!why.empty()) return fail(LCT_ERR_INVALID, why.c_str());
 
     lct_plan* p = new (std::nothrow) lct_plan();
     if (!p) return fail(LCT_ERR_NOMEM, "plan allocation");
     p->M = M; p->N = N; p->device = d->device;
     const size_t nfilt = (size_t)(M + 1) * 4 * N * N;
 #define LCT_TRY(expr) do { rc = (expr); if (rc) { lct_plan_destroy(p); return rc; } } while (0)
-    LCT_TRY(to_device(d->mtx_rowptr, (size_t)M + 1, &p->mtx_rowptr));
-    LCT_TRY(to_device(d->mtx_colidx, (size_t)nnz, &p->mtx_colidx));
-    LCT_TRY(to_device(d->mtx_vals, (size_t)nnz, &p->mtx_vals));
-    LCT_TRY(to_device(vals_f.data(), (size_t)nnz, &p->mtx_vals_falloff));
-    LCT_TRY(to_device(t_rowptr.data(), (size_t)M + 1, &p->mtxi_rowptr));
-    LCT_TRY(to_device(t_colidx.data(), (size_t)nnz, &p->mtxi_colidx));
-    LCT_TRY(to_device(t_vals.data(), (size_t)nnz, &p->mtxi_vals));
-    LCT_TRY(to_device(t_vals_f.data(), (size_t)nnz, &p->mtxi_vals_falloff));
+    LCT_TRY(upload_band(ht.mtx_ell_falloff, ht.mtx_rowptr, ht.mtx_vals_falloff, p->mtx_falloff));
+    LCT_TRY(upload_band(ht.mtx_ell, ht.mtx_rowptr, ht.mtx_vals, p->mtx));
+    LCT_TRY(upload_band(ht.mtxi_ell, ht.mtxi_rowptr, ht.mtxi_vals, p->mtxi));
+    LCT_TRY(upload_band(ht.mtxi_ell_falloff, ht.mtxi_rowptr, ht.mtxi_vals_falloff, p->mtxi_falloff));
     LCT_TRY(to_device(reinterpret_cast<const float2*>(d->filter_half), nfilt, &p->filt));
 #undef LCT_TRY
     // fold torch.ifft's 1/(2M*2N*2N) (tflct.py:151) into the filter; a power of two, so exact
@@ -222,6 +218,7 @@ static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const 
                void* const* events = nullptr) {
     if (!plan || !in || !out || !tbe || !ten || !ws) return fail(LCT_ERR_INVALID, "null argument");
     if (B <= 0 || D <= 0 || Tin <= 0 || Tin > plan->M) return fail(LCT_ERR_INVALID, "bad shape");
+    if (((uintptr_t)in | (uintptr_t)out | (uintptr_t)ws) & 15) return fail(LCT_ERR_INVALID, "buffers must be 16-byte aligned");
     bool uniform = true;
     for (int b = 0; b < B; ++b) {
         if (tbe[b] < 0 || ten[b] > plan->M || ten[b] - tbe[b] != Tin) return fail(LCT_ERR_INVALID, "bad time window");

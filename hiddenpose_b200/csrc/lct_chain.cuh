@@ -76,14 +76,13 @@ template <int N, class Launcher> int launch_col_filter(const Params& p, Launcher
         default: rc = -1;                                       \
     }
 
-// Resampling-operator tables the chain needs (device pointers on the GPU).
+// Resampling-operator tables the chain needs (device pointers on the GPU; see lct_tables.h).
+struct BandTable { const float4* ell; const int* rowptr; const float* vals; };
 struct ChainTables {
-    const int *mtx_rowptr, *mtx_colidx;        // CSR of mtx (M x M), rows = resampled bin
-    const float *mtx_vals_falloff;             // mtx[i][j] * falloff[j]      (forward K1)
-    const float *mtx_vals;                     // mtx[i][j]                   (backward K1)
-    const int *mtxi_rowptr, *mtxi_colidx;      // CSR of mtxi = mtx^T, rows = output bin
-    const float *mtxi_vals;                    // mtxi[j][i]                  (forward K5)
-    const float *mtxi_vals_falloff;            // mtxi[j][i] * falloff[j]     (backward K5)
+    BandTable mtx_falloff;      // mtx[i][j] * falloff[j]     forward  K1
+    BandTable mtx;              // mtx[i][j]                  backward K1
+    BandTable mtxi;             // mtxi[j][i]                 forward  K5
+    BandTable mtxi_falloff;     // mtxi[j][i] * falloff[j]    backward K5
     const float2* filt;
 };
 
@@ -105,8 +104,8 @@ int run_chain(Launcher& l, const ChainTables& t, int M, int N, int C, int D, int
         p.in_T = backward ? M : Tin;
         p.be_uniform = backward ? 0 : be_uniform;
         p.be_dev = backward ? nullptr : be_dev;
-        p.rowptr = t.mtx_rowptr; p.colidx = t.mtx_colidx;
-        p.vals = backward ? t.mtx_vals : t.mtx_vals_falloff;
+        const BandTable& bt = backward ? t.mtx : t.mtx_falloff;
+        p.ell = bt.ell; p.rowptr = bt.rowptr; p.vals = bt.vals;
         LCT_SWITCH_M(M, (launch_time_fwd<kM>(p, l)));
         if (rc) return rc;
     }
@@ -130,8 +129,8 @@ int run_chain(Launcher& l, const ChainTables& t, int M, int N, int C, int D, int
         p.out_T = backward ? Tin : M;
         p.be_uniform = backward ? be_uniform : 0;
         p.be_dev = backward ? be_dev : nullptr;
-        p.rowptr = t.mtxi_rowptr; p.colidx = t.mtxi_colidx;
-        p.vals = backward ? t.mtxi_vals_falloff : t.mtxi_vals;
+        const BandTable& bt = backward ? t.mtxi_falloff : t.mtxi;
+        p.ell = bt.ell; p.rowptr = bt.rowptr; p.vals = bt.vals;
         LCT_SWITCH_M(M, (launch_time_inv<kM>(p, l)));
         if (rc) return rc;
     }

@@ -14,11 +14,13 @@
 
 #ifdef LCT_EMULATE
 #include <cmath>
+#include <cstring>
 #include <vector_types.h>
 #define LCT_DEV inline
 #define LCT_HD inline
 #define LCT_UNROLL
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 #else
 #include <cuda_runtime.h>
 #define LCT_DEV __device__ __forceinline__

@@ -54,11 +54,35 @@ struct Params {
     float2* s2;                 // (C, M+1, 2N, N)
     const float2* filt;         // (M+1, 2N, 2N), already scaled by 1/(8 M N N)
     int conj_filter;
-    // CSR of the resampling operator used by this launch (mtx rows for K1, mtxi rows for K5)
+    // Resampling operator used by this launch (mtx rows for K1, mtxi rows for K5): one 16-byte
+    // record per row {start | len << 16, w0, w1, w2} (lct_tables.h); rows longer than 3
+    // continue in vals[rowptr[row] + 3 ...].
+    const float4* ell;
     const int* rowptr;
-    const int* colidx;
     const float* vals;
 };
+
+#ifdef LCT_EMULATE
+static inline int float_bits(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+#else
+LCT_DEV int float_bits(float f) { return __float_as_int(f); }
+#endif
+
+// sum_e w[e] * src[(start + e) * stride] for one operator row; `src` must have two readable
+// (finite) rows past the last one, because short rows still touch three.
+LCT_DEV float band_dot(const Params& p, int row, const float* src, int stride) {
+    const float4 e = LCT_LDG(p.ell + row);
+    const int sl = float_bits(e.x), start = sl & 0xffff, len = sl >> 16;
+    const float* s = src + start * stride;
+    float acc = e.y * s[0];
+    acc = fmaf(e.z, s[stride], acc);
+    acc = fmaf(e.w, s[2 * stride], acc);
+    if (len > 3) {
+        const float* v = p.vals + LCT_LDG(p.rowptr + row);
+        for (int k = 3; k < len; ++k) acc = fmaf(LCT_LDG(v + k), s[k * stride], acc);
+    }
+    return acc;
+}
 
 LCT_DEV int window_begin(const Params& p, int c) {
     return p.be_dev ? LCT_LDG(p.be_dev + (p.c_base + c) / p.D) : p.be_uniform;
@@ -73,6 +97,9 @@ template <class P, int CT_> struct TimeFwd {
     static constexpr int M = P::L, CT = CT_, kThreads = P::TL * CT;
     static constexpr int kPhases = 3 + (P::S - 1) + 1;
     static constexpr size_t kSmem = (size_t)M * CT * sizeof(float2);
+    static_assert((size_t)(M + 2) * CT * sizeof(float) <= kSmem, "x tile must fit");
+    static constexpr bool kWarpSync = false;
+    static constexpr int kMinBlocks = (kThreads <= 512) ? 2 : 1;
     struct Regs { float2 a[P::E]; };
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N * p.N / CT; gy = p.C; }
     static int iterations(const Params&) { return 1; }
@@ -83,24 +110,28 @@ template <class P, int CT_> struct TimeFwd {
         float* xs = reinterpret_cast<float*>(smem);
         float2* zs = reinterpret_cast<float2*>(smem);
         if constexpr (PH == 0) {
-            const float* src = p.in + (size_t)c * p.in_T * NN + col0;
-            for (int i = tid; i < p.in_T * CT; i += kThreads) {
-                const int t = i / CT, cc = i % CT;
-                xs[i] = LCT_LDG(src + (size_t)t * NN + cc);
+            // x tile -> xs[(M+2)][CT] f32, zero outside the window [be, en) and in the two pad rows
+            const int be = window_begin(p, c), en = be + p.in_T;
+            constexpr int V4 = CT / 4, kSlots = (M + 2) * V4;
+            const float4* src = reinterpret_cast<const float4*>(p.in + (size_t)c * p.in_T * NN + col0);
+            float4* xs4 = reinterpret_cast<float4*>(smem);
+            float4 v[(kSlots + kThreads - 1) / kThreads];
+            LCT_UNROLL
+            for (int u = 0; u < (kSlots + kThreads - 1) / kThreads; ++u) {
+                const int i = tid + u * kThreads, t = i / V4, q = i % V4;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t >= be && t < en) v[u] = LCT_LDG(src + (size_t)(t - be) * (NN / 4) + q);
+            }
+            LCT_UNROLL
+            for (int u = 0; u < (kSlots + kThreads - 1) / kThreads; ++u) {
+                const int i = tid + u * kThreads;
+                if (i < kSlots) xs4[i] = v[u];
             }
         } else if constexpr (PH == 1) {
-            const int be = window_begin(p, c), en = be + p.in_T;
-            auto u_at = [&](int i) -> float {
-                float acc = 0.f;
-                const int e0 = LCT_LDG(p.rowptr + i), e1 = LCT_LDG(p.rowptr + i + 1);
-                for (int e = e0; e < e1; ++e) {
-                    const int j = LCT_LDG(p.colidx + e);
-                    if (j >= be && j < en) acc += LCT_LDG(p.vals + e) * xs[(j - be) * CT + col];
-                }
-                return acc;
-            };
             fwd_stage<P, 0, true, TwConst>(tau,
-                [&](int pos, int) { return make_float2(u_at(2 * pos), u_at(2 * pos + 1)); },
+                [&](int pos, int) {
+                    return make_float2(band_dot(p, 2 * pos, xs + col, CT), band_dot(p, 2 * pos + 1, xs + col, CT));
+                },
                 [&](int, int slot, float2 v) { r.a[slot] = v; });
         } else if constexpr (PH == 2) {
             for_each_slot<P, 0>(tau, [&](int pos, int slot) { zs[pos * CT + col] = r.a[slot]; });
@@ -132,6 +163,8 @@ template <class P, int CT_> struct TimeInv {
     static constexpr int M = P::L, CT = CT_, kThreads = P::TL * CT;
     static constexpr int kPhases = 2 + P::S + 2;          // load | stage S-1 -> regs | scatter | middle.. | stage 0 -> regs | scatter vol | gather
     static constexpr size_t kSmem = (size_t)(M + 1) * CT * sizeof(float2);
+    static constexpr bool kWarpSync = false;
+    static constexpr int kMinBlocks = (kThreads <= 512) ? 2 : 1;
     struct Regs { float2 a[P::E]; };
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N * p.N / CT; gy = p.C; }
     static int iterations(const Params&) { return 1; }
@@ -143,10 +176,20 @@ template <class P, int CT_> struct TimeInv {
         float* vol = reinterpret_cast<float*>(smem);
         constexpr int SL = P::S - 1;
         if constexpr (PH == 0) {
-            const float2* src = p.s1 + (size_t)c * (M + 1) * NN + col0;
-            for (int i = tid; i < (M + 1) * CT; i += kThreads) {
-                const int k = i / CT, cc = i % CT;
-                zs[i] = src[(size_t)k * NN + cc];
+            // spectrum tile -> zs[(M+1)][CT] c64 (128-bit loads: two columns per lane)
+            constexpr int V2 = CT / 2, kSlots = (M + 1) * V2;
+            const float4* src = reinterpret_cast<const float4*>(p.s1 + (size_t)c * (M + 1) * NN + col0);
+            float4* zs4 = reinterpret_cast<float4*>(smem);
+            float4 v[(kSlots + kThreads - 1) / kThreads];
+            LCT_UNROLL
+            for (int u = 0; u < (kSlots + kThreads - 1) / kThreads; ++u) {
+                const int i = tid + u * kThreads, k = i / V2, q = i % V2;
+                if (i < kSlots) v[u] = src[(size_t)k * (NN / 2) + q];
+            }
+            LCT_UNROLL
+            for (int u = 0; u < (kSlots + kThreads - 1) / kThreads; ++u) {
+                const int i = tid + u * kThreads;
+                if (i < kSlots) zs4[i] = v[u];
             }
         } else if constexpr (PH == 1) {
             // Z[k] = (X[k] + conj X[M-k]) + i conj(w^k) (X[k] - conj X[M-k])
@@ -171,6 +214,7 @@ template <class P, int CT_> struct TimeInv {
                     vol[(2 * pos) * CT + col] = r.a[slot].x;
                     vol[(2 * pos + 1) * CT + col] = r.a[slot].y;
                 });
+                if (tau == 0) { vol[M * CT + col] = 0.f; vol[(M + 1) * CT + col] = 0.f; }
             } else {
                 for_each_slot<P, SL>(tau, [&](int pos, int slot) { zs[pos * CT + col] = r.a[slot]; });
             }
@@ -188,16 +232,11 @@ template <class P, int CT_> struct TimeInv {
                 vol[(2 * pos) * CT + col] = r.a[slot].x;
                 vol[(2 * pos + 1) * CT + col] = r.a[slot].y;
             });
+            if (tau == 0) { vol[M * CT + col] = 0.f; vol[(M + 1) * CT + col] = 0.f; }   // pad rows for band_dot
         } else if constexpr (PH == kPhases - 1) {
             const int be = window_begin(p, c);
             float* dst = p.out + (size_t)c * p.out_T * NN + col0 + col;
-            for (int j = tau; j < p.out_T; j += P::TL) {
-                const int row = be + j;
-                float acc = 0.f;
-                const int e0 = LCT_LDG(p.rowptr + row), e1 = LCT_LDG(p.rowptr + row + 1);
-                for (int e = e0; e < e1; ++e) acc += LCT_LDG(p.vals + e) * vol[LCT_LDG(p.colidx + e) * CT + col];
-                dst[(size_t)j * NN] = acc;
-            }
+            for (int j = tau; j < p.out_T; j += P::TL) dst[(size_t)j * NN] = band_dot(p, be + j, vol + col, CT);
         }
     }
 };
@@ -208,6 +247,8 @@ template <class P, int CT_> struct TimeInv {
 template <class P, int CT_> struct RowFwd {
     static constexpr int L = P::L, N = L / 2, CT = CT_, kThreads = P::TL * CT;
     static constexpr int kPhases = P::S;
+    static constexpr bool kWarpSync = false;
+    static constexpr int kMinBlocks = (kThreads >= 1024) ? 1 : ((1024 / kThreads) > 32 ? 32 : (1024 / kThreads));   // <= 64 regs
     static constexpr size_t kSmem = (P::S > 1) ? (size_t)L * CT * sizeof(float2) : 0;
     struct Regs {};
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N / CT; gy = p.C * (p.M + 1); }
@@ -240,6 +281,8 @@ template <class P, int CT_> struct RowFwd {
 template <class P, int CT_> struct RowInv {
     static constexpr int L = P::L, N = L / 2, CT = CT_, kThreads = P::TL * CT;
     static constexpr int kPhases = P::S;
+    static constexpr bool kWarpSync = false;
+    static constexpr int kMinBlocks = (kThreads >= 1024) ? 1 : ((1024 / kThreads) > 32 ? 32 : (1024 / kThreads));   // <= 64 regs
     static constexpr size_t kSmem = (P::S > 1) ? (size_t)L * CT * sizeof(float2) : 0;
     struct Regs {};
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N / CT; gy = p.C * (p.M + 1); }
@@ -274,23 +317,42 @@ template <class P, int CT_> struct RowInv {
 // ---------------------------------------------------------------------------
 template <class P, int RB_> struct ColFilter {
     static_assert(P::S == 2, "ColFilter needs a two-stage plan");
+    static_assert(32 % P::TL == 0, "the threads of one line must share a warp");
     static constexpr int L = P::L, N = L / 2, RB = RB_, kThreads = P::TL * RB;
     static constexpr int kPhases = 3;
+    // all threads of a line sit in one warp (tid % TL), so the exchanges only need __syncwarp:
+    // warps run through the channel loop independently of each other.
+    static constexpr bool kWarpSync = true;
+    static constexpr int kMinBlocks = (P::E <= 16) ? 2 : 1;
     static constexpr int PAD = 1;
     static constexpr int RS = L + P::R0 * PAD + ((P::TL < 16) ? 8 : 0);    // row stride in float2
     static constexpr size_t kSmem = (size_t)RB * RS * sizeof(float2);
-    struct Regs { float2 w[P::E]; };
+    static constexpr int kIn = P::E / 2;                                   // non-zero inputs per thread
+    struct Regs { float2 w[P::E]; float2 pre[kIn]; };
     static void grid(const Params& p, int& gx, int& gy) { gx = L / RB; gy = p.M + 1; }
     static int iterations(const Params& p) { return p.C; }
     static LCT_DEV int padpos(int pos) { return pos + (pos / P::st(0)) * PAD; }
+
+    // loads the thread's share of one input row (positions < N) into r.pre
+    static LCT_DEV void fetch(const float2* row, int tau, Regs& r) {
+        constexpr int r0 = P::R0, str = P::st(0), NB = L / r0;
+        LCT_UNROLL
+        for (int m = 0; m < NB / P::TL; ++m) {
+            const int lo = tau + m * P::TL;
+            LCT_UNROLL
+            for (int q = 0; q < r0 / 2; ++q) r.pre[m * (r0 / 2) + q] = row[lo + q * str];
+        }
+    }
 
     template <int PH> static LCT_DEV void phase(const Params& p, Regs& r, unsigned char* smem, int tid, int bx, int by, int it) {
         const int tau = tid % P::TL, rl = tid / P::TL;
         const int kh = bx * RB + rl, kt = by, c = it;
         float2* zs = reinterpret_cast<float2*>(smem) + rl * RS;
-        float2* row = p.s2 + (((size_t)c * (p.M + 1) + kt) * L + kh) * N;
+        const size_t chan = (size_t)(p.M + 1) * L * N;
+        float2* row = p.s2 + (size_t)c * chan + ((size_t)kt * L + kh) * N;
         if constexpr (PH == 0) {
             if (it == 0) {
+                fetch(row, tau, r);
                 const float2* f = p.filt + ((size_t)kt * L + kh) * L;
                 for_each_slot<P, 1>(tau, [&](int pos, int slot) {
                     float2 w = LCT_LDG(f + P::pos_to_freq(pos));
@@ -298,9 +360,11 @@ template <class P, int RB_> struct ColFilter {
                     r.w[slot] = w;
                 });
             }
+            constexpr int r0 = P::R0;
             fwd_stage<P, 0, true, TwGlobal>(tau,
-                [&](int pos, int) { return row[pos]; },
+                [&](int, int slot) { return r.pre[(slot / r0) * (r0 / 2) + (slot % r0)]; },
                 [&](int pos, int, float2 v) { zs[padpos(pos)] = v; });
+            if (it + 1 < p.C) fetch(row + chan, tau, r);        // next channel's row flies during this one's math
         } else if constexpr (PH == 1) {
             float2 a[P::E];
             fwd_stage<P, 1, false, TwGlobal>(tau,
@@ -324,12 +388,12 @@ template <class P, int RB_> struct ColFilter {
 template <class K, int PH> struct PhaseLoop {
     static LCT_DEV void run(const Params& p, typename K::Regs& r, unsigned char* smem, int it) {
         K::template phase<PH>(p, r, smem, threadIdx.x, blockIdx.x, blockIdx.y, it);
-        __syncthreads();
+        if constexpr (K::kWarpSync) __syncwarp(); else __syncthreads();
         if constexpr (PH + 1 < K::kPhases) PhaseLoop<K, PH + 1>::run(p, r, smem, it);
     }
 };
 
-template <class K> __global__ void __launch_bounds__(K::kThreads) lct_kernel(const Params p, const int iters) {
+template <class K> __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) lct_kernel(const Params p, const int iters) {
     extern __shared__ __align__(16) unsigned char smem[];
     typename K::Regs r;
     for (int it = 0; it < iters; ++it) PhaseLoop<K, 0>::run(p, r, smem, it);

@@ -1,0 +1,93 @@
+// Host-side construction of the resampling tables the kernels read.
+// Shared by the CUDA library (lct_api.cu) and the CPU thread emulator (tests/emu).
+//
+// The reference applies mtx / mtxi = mtx^T as dense M x M matmuls
+// (/root/reference/models/tflct.py:135-138,156-159).  Both are staircase band matrices
+// (utils/helper.py:35-69): every row is one contiguous run of columns, nearly always of
+// length <= 3.  Each row is therefore stored as one 16-byte record
+//     { start | (len << 16),  w0, w1, w2 }
+// read with a single 128-bit load and applied branch-free; only the few longer rows
+// (the first ~sqrt(M) rows of mtx) continue into the CSR value array.
+#pragma once
+
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace lct {
+
+struct EllRow { int32_t start_len; float w[3]; };   // 16 bytes, loaded as float4
+
+struct HostTables {
+    int M = 0;
+    // mtx rows (K1): band start/len + values with and without the falloff folded in
+    std::vector<int32_t> mtx_rowptr;
+    std::vector<float> mtx_vals_falloff, mtx_vals;
+    std::vector<EllRow> mtx_ell_falloff, mtx_ell;
+    // mtxi rows (K5)
+    std::vector<int32_t> mtxi_rowptr;
+    std::vector<float> mtxi_vals, mtxi_vals_falloff;
+    std::vector<EllRow> mtxi_ell, mtxi_ell_falloff;
+};
+
+inline std::vector<EllRow> make_ell(int M, const std::vector<int32_t>& rowptr, const std::vector<int32_t>& start,
+                                    const std::vector<float>& vals) {
+    std::vector<EllRow> ell(M);
+    for (int i = 0; i < M; ++i) {
+        const int len = rowptr[i + 1] - rowptr[i];
+        ell[i].start_len = (len > 0 ? start[i] : 0) | (len << 16);
+        for (int e = 0; e < 3; ++e) ell[i].w[e] = (e < len) ? vals[rowptr[i] + e] : 0.0f;
+    }
+    return ell;
+}
+
+// Returns "" on success, otherwise a description of what is wrong with the operator.
+inline std::string build_tables(int M, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                                const float* falloff /* M or null */, HostTables& t) {
+    t.M = M;
+    if (rowptr[0] != 0) return "CSR row pointers must start at 0";
+    const int nnz = rowptr[M];
+    if (nnz <= 0) return "empty operator";
+    std::vector<float> fall(M, 1.0f);
+    if (falloff) std::memcpy(fall.data(), falloff, sizeof(float) * M);
+    std::vector<int32_t> start(M, 0), t_start(M, M), t_count(M, 0), t_last(M, -1);
+    for (int i = 0; i < M; ++i) {
+        if (rowptr[i + 1] < rowptr[i]) return "CSR row pointers not monotone";
+        for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+            const int j = colidx[e];
+            if (j < 0 || j >= M) return "CSR column index out of range";
+            if (e == rowptr[i]) start[i] = j;
+            else if (j != colidx[e - 1] + 1) return "operator rows must be contiguous column runs";
+            if (t_count[j] == 0) t_start[j] = i;
+            else if (i != t_last[j] + 1) return "operator columns must be contiguous row runs";
+            t_last[j] = i;
+            t_count[j]++;
+        }
+    }
+    t.mtx_rowptr.assign(rowptr, rowptr + M + 1);
+    t.mtx_vals.assign(vals, vals + nnz);
+    t.mtx_vals_falloff.resize(nnz);
+    for (int e = 0; e < nnz; ++e) t.mtx_vals_falloff[e] = vals[e] * fall[colidx[e]];   // x*gridz^p (tflct.py:123-127)
+    t.mtx_ell = make_ell(M, t.mtx_rowptr, start, t.mtx_vals);
+    t.mtx_ell_falloff = make_ell(M, t.mtx_rowptr, start, t.mtx_vals_falloff);
+
+    // transpose: mtxi = mtx^T (helper.py:61)
+    t.mtxi_rowptr.assign(M + 1, 0);
+    for (int j = 0; j < M; ++j) t.mtxi_rowptr[j + 1] = t.mtxi_rowptr[j] + t_count[j];
+    t.mtxi_vals.assign(nnz, 0.f);
+    t.mtxi_vals_falloff.assign(nnz, 0.f);
+    std::vector<int32_t> cursor(t.mtxi_rowptr.begin(), t.mtxi_rowptr.end() - 1);
+    for (int i = 0; i < M; ++i)
+        for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+            const int j = colidx[e], dst = cursor[j]++;
+            t.mtxi_vals[dst] = vals[e];
+            t.mtxi_vals_falloff[dst] = vals[e] * fall[j];      // backward: falloff applied to the output bin
+        }
+    for (int j = 0; j < M; ++j) if (t_count[j] == 0) t_start[j] = 0;
+    t.mtxi_ell = make_ell(M, t.mtxi_rowptr, t_start, t.mtxi_vals);
+    t.mtxi_ell_falloff = make_ell(M, t.mtxi_rowptr, t_start, t.mtxi_vals_falloff);
+    return "";
+}
+
+}  // namespace lct

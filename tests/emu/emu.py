@@ -42,11 +42,8 @@ class EmuPlan:
     def __init__(self, N, M, bin_len, wall_size=2.0, method="lct", material="diffuse"):
         self.N, self.M = N, M
         rp, ci, v = ops.resampling_csr(M)
-        fo = ops.falloff(M, material)
-        self.mtx = (rp, ci, (v * fo[ci]).astype(np.float32), v)
-        trp, tci, tv = ops.csr_transpose(rp, ci, v, M)
-        rows = np.repeat(np.arange(M), np.diff(trp))
-        self.mtxi = (trp, tci, tv, (tv * fo[rows]).astype(np.float32))
+        self.csr = (np.ascontiguousarray(rp, np.int32), np.ascontiguousarray(ci, np.int32), np.ascontiguousarray(v, np.float32))
+        self.falloff = np.ascontiguousarray(ops.falloff(M, material), np.float32)
         w = ops.inverse_filter_half(N, M, ops.slope_for(M, bin_len, wall_size), method)
         self.filt = np.ascontiguousarray((w * np.float32(1.0 / (8.0 * M * N * N))).astype(np.complex64))
 
@@ -68,8 +65,7 @@ class EmuPlan:
         rc = lib(reverse).lct_emu_run(
             M, N, C, D, Tin, int(be[0]), None if uniform else _p(be, i32),
             _p(inp, f), _p(out, f), _p(s1.view(np.float32), f), _p(s2.view(np.float32), f),
-            _p(self.mtx[0], i32), _p(self.mtx[1], i32), _p(self.mtx[2], f), _p(self.mtx[3], f),
-            _p(self.mtxi[0], i32), _p(self.mtxi[1], i32), _p(self.mtxi[2], f), _p(self.mtxi[3], f),
+            _p(self.csr[0], i32), _p(self.csr[1], i32), _p(self.csr[2], f), _p(self.falloff, f),
             _p(self.filt.view(np.float32), f), int(backward), int(mask))
         assert rc == 0, rc
         return out, s1, s2

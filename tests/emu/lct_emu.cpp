@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "lct_chain.cuh"
+#include "lct_tables.h"
 
 namespace lct {
 float2 h_tw[kTwN];
@@ -62,14 +63,19 @@ void lct_emu_init(int reverse_threads) {
     }
 }
 
-// All pointers are host pointers.  `filt` must already carry the 1/(8 M N N) scale.
+// All pointers are host pointers.  `filt` must already carry the 1/(8 M N N) scale.  The operator
+// arrives as the CSR of mtx plus the falloff vector, exactly as lct_plan_create receives it.
 int lct_emu_run(int M, int N, int C, int D, int Tin, int be_uniform, const int* be,
                 const float* in, float* out, float* s1, float* s2,
-                const int* mtx_rowptr, const int* mtx_colidx, const float* mtx_vals_falloff, const float* mtx_vals,
-                const int* mtxi_rowptr, const int* mtxi_colidx, const float* mtxi_vals, const float* mtxi_vals_falloff,
+                const int* mtx_rowptr, const int* mtx_colidx, const float* mtx_vals, const float* falloff,
                 const float* filt, int backward, int mask) {
-    lct::ChainTables t{mtx_rowptr, mtx_colidx, mtx_vals_falloff, mtx_vals,
-                       mtxi_rowptr, mtxi_colidx, mtxi_vals, mtxi_vals_falloff,
+    lct::HostTables ht;
+    if (!lct::build_tables(M, mtx_rowptr, mtx_colidx, mtx_vals, falloff, ht).empty()) return 100;
+    auto band = [](const std::vector<lct::EllRow>& e, const std::vector<int32_t>& rp, const std::vector<float>& v) {
+        return lct::BandTable{reinterpret_cast<const float4*>(e.data()), rp.data(), v.data()};
+    };
+    lct::ChainTables t{band(ht.mtx_ell_falloff, ht.mtx_rowptr, ht.mtx_vals_falloff), band(ht.mtx_ell, ht.mtx_rowptr, ht.mtx_vals),
+                       band(ht.mtxi_ell, ht.mtxi_rowptr, ht.mtxi_vals), band(ht.mtxi_ell_falloff, ht.mtxi_rowptr, ht.mtxi_vals_falloff),
                        reinterpret_cast<const float2*>(filt)};
     EmuLauncher l;
     return lct::run_chain(l, t, M, N, C, D, Tin, be_uniform, be, 0, in, out,
