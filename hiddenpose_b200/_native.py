@@ -15,7 +15,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
-LIB_PATH = os.path.join(PKG_DIR, "libhiddenpose_lct.so")
+LIB_PATH = os.environ.get("HIDDENPOSE_LCT_LIB") or os.path.join(PKG_DIR, "libhiddenpose_lct.so")   # override: A/B builds
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",

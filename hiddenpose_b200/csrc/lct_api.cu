@@ -124,10 +124,13 @@ struct DeviceBand {
 struct lct_plan {
     int M = 0, N = 0, device = 0;
     DeviceBand mtx_falloff, mtx, mtxi, mtxi_falloff;
-    float2* filt = nullptr;
-    size_t per_channel_bytes() const { return (size_t)(M + 1) * N * N * sizeof(float2) * 3; }
+    float2* filt = nullptr;         // natural layout (unfused K3), or
+    float2* filt_plane = nullptr;   // [kt][kw][plane row] (plane-fused kernel); exactly one of the two is set
+    bool fused() const { return filt_plane != nullptr; }
+    // S1 (C, M+1, N, N) c64, plus S2 (C, M+1, 2N, N) c64 when the middle stages are not fused
+    size_t per_channel_bytes() const { return (size_t)(M + 1) * N * N * sizeof(float2) * (fused() ? 1 : 3); }
     lct::ChainTables tables() const {
-        return lct::ChainTables{mtx_falloff.view(), mtx.view(), mtxi.view(), mtxi_falloff.view(), filt};
+        return lct::ChainTables{mtx_falloff.view(), mtx.view(), mtxi.view(), mtxi_falloff.view(), filt, filt_plane};
     }
 };
 
@@ -166,6 +169,7 @@ void lct_plan_destroy(lct_plan* plan) {
     DeviceGuard g(plan->device);
     plan->mtx_falloff.release(); plan->mtx.release(); plan->mtxi.release(); plan->mtxi_falloff.release();
     cudaFree(plan->filt);
+    cudaFree(plan->filt_plane);
     delete plan;
 }
 
@@ -195,10 +199,31 @@ int lct_plan_create(const lct_desc* d, lct_plan** out) {
     LCT_TRY(upload_band(ht.mtx_ell, ht.mtx_rowptr, ht.mtx_vals, p->mtx));
     LCT_TRY(upload_band(ht.mtxi_ell, ht.mtxi_rowptr, ht.mtxi_vals, p->mtxi));
     LCT_TRY(upload_band(ht.mtxi_ell_falloff, ht.mtxi_rowptr, ht.mtxi_vals_falloff, p->mtxi_falloff));
-    LCT_TRY(to_device(reinterpret_cast<const float2*>(d->filter_half), nfilt, &p->filt));
+    float2* dev_filt = nullptr;
+    if (lct::plane_fusable(N) && !(d->reserved & LCT_FLAG_NO_PLANE_FUSION)) {
+        // fused layout: [kt][kw][plane row], rows in the order the forward H stages leave them
+        const int L = 2 * N;
+        const float2* nat = reinterpret_cast<const float2*>(d->filter_half);
+        std::vector<float2> perm(nfilt);
+        std::vector<int> kh_of_row(L);
+        for (int r = 0; r < L; ++r) {
+            int rc = -1;
+            LCT_SWITCH_N(N, (lct::plane_row_freq<kN>(r)));
+            kh_of_row[r] = rc;
+        }
+        for (int kt = 0; kt <= M; ++kt)
+            for (int kw = 0; kw < L; ++kw)
+                for (int r = 0; r < L; ++r)
+                    perm[((size_t)kt * L + kw) * L + r] = nat[((size_t)kt * L + kh_of_row[r]) * L + kw];
+        LCT_TRY(to_device(perm.data(), nfilt, &p->filt_plane));
+        dev_filt = p->filt_plane;
+    } else {
+        LCT_TRY(to_device(reinterpret_cast<const float2*>(d->filter_half), nfilt, &p->filt));
+        dev_filt = p->filt;
+    }
 #undef LCT_TRY
     // fold torch.ifft's 1/(2M*2N*2N) (tflct.py:151) into the filter; a power of two, so exact
-    scale_filter_kernel<<<1024, 256>>>(p->filt, nfilt, 1.0f / (8.0f * (float)M * (float)N * (float)N));
+    scale_filter_kernel<<<1024, 256>>>(dev_filt, nfilt, 1.0f / (8.0f * (float)M * (float)N * (float)N));
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { lct_plan_destroy(p); return fail(LCT_ERR_CUDA, "filter scaling", e); }
     *out = p;

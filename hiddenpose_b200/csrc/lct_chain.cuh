@@ -9,6 +9,7 @@ namespace lct {
 // Column-batched plans (lanes run across columns; used along T with L = M and
 // along H with L = 2N).
 template <int L> struct ColPlan;
+template <> struct ColPlan<8>   { using type = Plan<4, 2>; };
 template <> struct ColPlan<16>  { using type = Plan<4, 4>; };
 template <> struct ColPlan<32>  { using type = Plan<8, 4>; };
 template <> struct ColPlan<64>  { using type = Plan<8, 8>; };
@@ -26,7 +27,10 @@ template <> struct LinePlan<256> { using type = Plan<16, 16>; };
 template <> struct LinePlan<512> { using type = Plan<32, 16>; };
 
 // column tile (in columns of the flattened H*W axis) for the T-axis kernels
-template <int M> struct TimeTile { static constexpr int CT = (M >= 512) ? 16 : 32; };
+#ifndef LCT_TIME_CT
+#define LCT_TIME_CT 32
+#endif
+template <int M> struct TimeTile { static constexpr int CT = (M >= 512) ? 16 : LCT_TIME_CT; };
 // column tile along W for the H-axis kernels
 template <int N> struct RowTile { static constexpr int CT = (N >= 256) ? 16 : (N < 32 ? N : 32); };
 // rows per block for K3
@@ -34,6 +38,20 @@ template <int N> struct LineRows {
     using P = typename LinePlan<2 * N>::type;
     static constexpr int RB = (256 / P::TL) < 2 * N ? (256 / P::TL) : 2 * N;
 };
+
+// plane-resident fusion of K2+K3+K4: the 2N x (N+1) c64 plane must fit in shared memory
+constexpr bool plane_fusable(int N) { return N <= 64; }
+#ifndef LCT_PLANE_THREADS
+#define LCT_PLANE_THREADS 512
+#endif
+template <int N> struct PlaneKernel {
+    using PHp = typename ColPlan<2 * N>::type;
+    static constexpr int kFull = N * PHp::TL;                               // one column batch
+    static constexpr int NT = kFull < LCT_PLANE_THREADS ? kFull : LCT_PLANE_THREADS;
+    using type = PlaneFilter<PHp, typename ColPlan<N>::type, NT>;
+};
+// H-frequency held by plane row r after the forward H stages (the fused filter is stored in this order)
+template <int N> int plane_row_freq(int r) { return ColPlan<2 * N>::type::pos_to_freq(r); }
 
 constexpr bool supported_M(int M) { return M == 32 || M == 64 || M == 128 || M == 256 || M == 512; }
 constexpr bool supported_N(int N) { return N == 8 || N == 16 || N == 32 || N == 64 || N == 128 || N == 256; }
@@ -54,6 +72,10 @@ template <int N, class Launcher> int launch_row_inv(const Params& p, Launcher& l
 }
 template <int N, class Launcher> int launch_col_filter(const Params& p, Launcher& l) {
     return l.template launch<ColFilter<typename LinePlan<2 * N>::type, LineRows<N>::RB>>(p);
+}
+template <int N, class Launcher> int launch_plane(const Params& p, Launcher& l) {
+    if constexpr (plane_fusable(N)) return l.template launch<typename PlaneKernel<N>::type>(p);
+    else return -1;
 }
 
 #define LCT_SWITCH_M(M, CALL)                                   \
@@ -83,7 +105,8 @@ struct ChainTables {
     BandTable mtx;              // mtx[i][j]                  backward K1
     BandTable mtxi;             // mtxi[j][i]                 forward  K5
     BandTable mtxi_falloff;     // mtxi[j][i] * falloff[j]    backward K5
-    const float2* filt;
+    const float2* filt;         // (M+1, 2N, 2N) natural order, for K3            (null if fused)
+    const float2* filt_plane;   // (M+1, 2N kw, 2N plane rows), for PlaneFilter   (null if not fused)
 };
 
 // Runs the stages selected in `mask` (all five for a real call).
@@ -110,6 +133,14 @@ int run_chain(Launcher& l, const ChainTables& t, int M, int N, int C, int D, int
         if (rc) return rc;
     }
     l.mark(1);
+    constexpr int kMiddle = kStageRowFwd | kStageColFilter | kStageRowInv;
+    if ((mask & kMiddle) == kMiddle && t.filt_plane) {
+        p.filt = t.filt_plane;
+        LCT_SWITCH_N(N, (launch_plane<kN>(p, l)));
+        if (rc) return rc;
+        l.mark(2); l.mark(3);
+        mask &= ~kMiddle;
+    }
     if (mask & kStageRowFwd) {
         LCT_SWITCH_N(N, (launch_row_fwd<kN>(p, l)));
         if (rc) return rc;

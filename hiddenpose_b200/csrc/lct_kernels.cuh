@@ -99,7 +99,7 @@ template <class P, int CT_> struct TimeFwd {
     static constexpr size_t kSmem = (size_t)M * CT * sizeof(float2);
     static_assert((size_t)(M + 2) * CT * sizeof(float) <= kSmem, "x tile must fit");
     static constexpr bool kWarpSync = false;
-    static constexpr int kMinBlocks = (kThreads <= 512) ? 2 : 1;
+    static constexpr int kMinBlocks = (kThreads >= 1024) ? 1 : 1024 / kThreads;     // 1024 threads/SM at <= 64 regs
     struct Regs { float2 a[P::E]; };
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N * p.N / CT; gy = p.C; }
     static int iterations(const Params&) { return 1; }
@@ -164,7 +164,7 @@ template <class P, int CT_> struct TimeInv {
     static constexpr int kPhases = 2 + P::S + 2;          // load | stage S-1 -> regs | scatter | middle.. | stage 0 -> regs | scatter vol | gather
     static constexpr size_t kSmem = (size_t)(M + 1) * CT * sizeof(float2);
     static constexpr bool kWarpSync = false;
-    static constexpr int kMinBlocks = (kThreads <= 512) ? 2 : 1;
+    static constexpr int kMinBlocks = (kThreads >= 1024) ? 1 : 1024 / kThreads;     // 1024 threads/SM at <= 64 regs
     struct Regs { float2 a[P::E]; };
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N * p.N / CT; gy = p.C; }
     static int iterations(const Params&) { return 1; }
@@ -377,6 +377,124 @@ template <class P, int RB_> struct ColFilter {
             inv_stage<P, 0, true, TwGlobal>(tau,
                 [&](int pos, int) { return zs[padpos(pos)]; },
                 [&](int pos, int, float2 v) { row[pos] = v; });
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Plane-resident fusion of K2 + K3 + K4 (N <= 64): one block owns one (c, kt) plane.
+// The zero-extended 2N x N half-transformed plane lives in shared memory (row stride N+1
+// float2, conflict-free for lanes along W and for lanes along H), so the plane is read
+// from and written to HBM exactly once: 16 B per spectrum element instead of 80 B.
+//   H forward  : K2's stages, lanes along W, output rows stay in plan position order.
+//   W pass     : per row, the 2N-point zero-extended FFT is two N-point FFTs (even / odd
+//                output frequencies, the odd one pre-rotated by w_2N^n); each is filtered and
+//                inverted in place in the row's own N slots, the two results recombined
+//                (y = y_even + conj(w_2N^n) y_odd).  Lanes run along H here, so twiddles are
+//                warp-uniform constant-bank reads and the filter, stored as [kt][kw][row], is
+//                read coalesced.
+//   H inverse  : K4's stages, written back over the input plane in S1.
+// ---------------------------------------------------------------------------
+template <class PHp, class PWp, int NT_> struct PlaneFilter {
+    static constexpr int L = PHp::L, N = L / 2;
+    static_assert(PWp::L == N && PWp::S == 2 && PHp::S == 2, "plane fusion needs two-stage plans");
+    static constexpr int kThreads = NT_;
+    static constexpr int CB = kThreads / PHp::TL;                // columns per H batch
+    static_assert(CB >= 1 && N % CB == 0, "column batches must tile the plane");
+    static constexpr int nHB = N / CB;
+    static constexpr int RBt = (kThreads / PWp::TL) < L ? (kThreads / PWp::TL) : L;   // rows per W batch
+    static_assert(L % RBt == 0, "row batches must tile the plane");
+    static constexpr int nWB = L / RBt;
+    static constexpr int RS = N + 1;
+    static constexpr size_t kSmem = (size_t)L * RS * sizeof(float2);
+    static constexpr int kPhases = 2 + nWB * 6 + 2;
+    static constexpr int EW = PWp::E;
+    static constexpr bool kWarpSync = false;
+#ifndef LCT_PLANE_MINBLOCKS
+#define LCT_PLANE_MINBLOCKS 2
+#endif
+    static constexpr int kMinBlocks = (LCT_PLANE_MINBLOCKS * kSmem <= 220 * 1024) ? LCT_PLANE_MINBLOCKS : 1;
+    struct Regs { float2 in[EW]; float2 acc[EW]; };
+    static void grid(const Params& p, int& gx, int& gy) { gx = p.C; gy = p.M + 1; }   // c fastest: filter plane reused from L2
+    static int iterations(const Params&) { return 1; }
+
+    // address of the filter value a W-pass thread needs for (plane row, N-point position, parity)
+    static LCT_DEV const float2* filt_at(const Params& p, int kt, int row, int pos, int par) {
+        return p.filt + ((size_t)kt * L + (2 * PWp::pos_to_freq(pos) + par)) * L + row;        // [kt][kw][row]
+    }
+
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs& r, unsigned char* smem, int tid, int bx, int by, int) {
+        float2* T = reinterpret_cast<float2*>(smem);
+        const int kt = by;
+        const size_t plane = (size_t)bx * (p.M + 1) + kt;
+        constexpr int kW0 = 2, kW1 = 2 + 6 * nWB;
+        if constexpr (PH < kW0) {
+            // H forward; column batches touch disjoint columns, so they share a phase
+            const int tau = tid / CB;
+            LCT_UNROLL
+            for (int hb = 0; hb < nHB; ++hb) {
+                const int col = hb * CB + tid % CB;
+                const float2* src = p.s1 + plane * N * N + col;
+                if constexpr (PH == 0) {
+                    fwd_stage<PHp, 0, true, TwConst>(tau,
+                        [&](int pos, int) { return src[(size_t)pos * N]; },
+                        [&](int pos, int, float2 v) { T[pos * RS + col] = v; });
+                } else {
+                    fwd_stage<PHp, 1, false, TwConst>(tau,
+                        [&](int pos, int) { return T[pos * RS + col]; },
+                        [&](int pos, int, float2 v) { T[pos * RS + col] = v; });
+                }
+            }
+        } else if constexpr (PH < kW1) {
+            constexpr int wb = (PH - kW0) / 6, step = (PH - kW0) % 6, par = step / 3, st3 = step % 3;
+            const int rl = tid % RBt, tau = tid / RBt, row = wb * RBt + rl;
+            const bool active = tid < RBt * PWp::TL;
+            float2* Tr = T + row * RS;
+            if (active) {
+                if constexpr (st3 == 0) {
+                    if constexpr (par == 0) {
+                        for_each_slot<PWp, 0>(tau, [&](int pos, int slot) { r.in[slot] = Tr[pos]; });
+                    }
+                    fwd_stage<PWp, 0, false, TwConst>(tau,
+                        [&](int pos, int slot) {
+                            return par == 0 ? r.in[slot] : cmul(r.in[slot], TwConst::get(pos * (kTwN / L)));
+                        },
+                        [&](int pos, int, float2 v) { Tr[pos] = v; });
+                } else if constexpr (st3 == 1) {
+                    float2 w[EW], b[EW];
+                    for_each_slot<PWp, 1>(tau, [&](int pos, int slot) { w[slot] = LCT_LDG(filt_at(p, kt, row, pos, par)); });
+                    fwd_stage<PWp, 1, false, TwConst>(tau,
+                        [&](int pos, int) { return Tr[pos]; },
+                        [&](int, int slot, float2 v) { b[slot] = p.conj_filter ? cmulc(v, w[slot]) : cmul(v, w[slot]); });
+                    inv_stage<PWp, 1, false, TwConst>(tau,
+                        [&](int, int slot) { return b[slot]; },
+                        [&](int pos, int, float2 v) { Tr[pos] = v; });
+                } else {
+                    inv_stage<PWp, 0, false, TwConst>(tau,
+                        [&](int pos, int) { return Tr[pos]; },
+                        [&](int pos, int slot, float2 v) {
+                            if constexpr (par == 0) r.acc[slot] = v;
+                            else Tr[pos] = cadd(r.acc[slot], cmulc(v, TwConst::get(pos * (kTwN / L))));
+                        });
+                }
+            }
+        } else {
+            constexpr int s = PH - kW1;
+            const int tau = tid / CB;
+            LCT_UNROLL
+            for (int hb = 0; hb < nHB; ++hb) {
+                const int col = hb * CB + tid % CB;
+                float2* dst = p.s1 + plane * N * N + col;
+                if constexpr (s == 0) {
+                    inv_stage<PHp, 1, false, TwConst>(tau,
+                        [&](int pos, int) { return T[pos * RS + col]; },
+                        [&](int pos, int, float2 v) { T[pos * RS + col] = v; });
+                } else {
+                    inv_stage<PHp, 0, true, TwConst>(tau,
+                        [&](int pos, int) { return T[pos * RS + col]; },
+                        [&](int pos, int, float2 v) { dst[(size_t)pos * N] = v; });
+                }
+            }
         }
     }
 };

@@ -22,7 +22,7 @@ def _i32_array(values):
 class LctPlan:
     """Owns one ``lct_plan*`` (immutable device constants) on one CUDA device."""
 
-    def __init__(self, M, N, csr, falloff, filter_half, device, lapw=None, workspace_limit_bytes=16 << 30):
+    def __init__(self, M, N, csr, falloff, filter_half, device, lapw=None, workspace_limit_bytes=16 << 30, flags=0):
         if device.type != "cuda":
             raise RuntimeError("LctPlan needs a CUDA device; there is no CPU implementation of this layer")
         self.lib = _native.load()
@@ -39,7 +39,7 @@ class LctPlan:
         f32p, i32p = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
         desc = _native.LctDesc(
             time_bins=M, spatial=N, device=device.index if device.index is not None else torch.cuda.current_device(),
-            reserved=0, mtx_rowptr=rowptr.ctypes.data_as(i32p), mtx_colidx=colidx.ctypes.data_as(i32p),
+            reserved=int(flags), mtx_rowptr=rowptr.ctypes.data_as(i32p), mtx_colidx=colidx.ctypes.data_as(i32p),
             mtx_vals=vals.ctypes.data_as(f32p), falloff=None if fall is None else fall.ctypes.data_as(f32p),
             filter_half=filt.view(np.float32).ctypes.data_as(f32p))
         handle = ctypes.c_void_p()

@@ -42,6 +42,9 @@ extern "C" {
 
 #define LCT_ABI_VERSION 1
 
+/* lct_desc.flags */
+#define LCT_FLAG_NO_PLANE_FUSION 1   /* keep K2/K3/K4 as three kernels even when the plane fits on chip */
+
 typedef struct lct_plan lct_plan;
 
 /* Operators, all in HOST memory, copied to the device by lct_plan_create. */
@@ -49,7 +52,7 @@ typedef struct lct_desc {
     int32_t time_bins;          /* M: `crop` / `time_size`; power of two in [32, 512]            */
     int32_t spatial;            /* N: `spatial` / `image_size` (H == W); power of two in [8, 256] */
     int32_t device;             /* CUDA device ordinal                                            */
-    int32_t reserved;           /* must be 0                                                      */
+    int32_t reserved;           /* flags: 0 or LCT_FLAG_*                                         */
     const int32_t* mtx_rowptr;  /* M+1   CSR row pointers of mtx (helper.py:35-69)                */
     const int32_t* mtx_colidx;  /* nnz                                                            */
     const float* mtx_vals;      /* nnz                                                            */

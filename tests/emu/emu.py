@@ -46,8 +46,12 @@ class EmuPlan:
         self.falloff = np.ascontiguousarray(ops.falloff(M, material), np.float32)
         w = ops.inverse_filter_half(N, M, ops.slope_for(M, bin_len, wall_size), method)
         self.filt = np.ascontiguousarray((w * np.float32(1.0 / (8.0 * M * N * N))).astype(np.complex64))
+        # fused layout [kt][kw][plane row], rows in the H plan's position order (what lct_plan_create builds)
+        L = 2 * N
+        kh = np.array([lib().lct_emu_plane_row_freq(N, r) for r in range(L)])
+        self.filt_plane = np.ascontiguousarray(self.filt[:, kh, :].transpose(0, 2, 1)) if N <= 64 else None
 
-    def run(self, inp, D, Tin, be, backward=False, mask=31, reverse=False, s1=None, s2=None):
+    def run(self, inp, D, Tin, be, backward=False, mask=31, reverse=False, s1=None, s2=None, fused=True):
         M, N = self.M, self.N
         inp = np.ascontiguousarray(inp, dtype=np.float32)
         C = inp.shape[0]
@@ -66,6 +70,8 @@ class EmuPlan:
             M, N, C, D, Tin, int(be[0]), None if uniform else _p(be, i32),
             _p(inp, f), _p(out, f), _p(s1.view(np.float32), f), _p(s2.view(np.float32), f),
             _p(self.csr[0], i32), _p(self.csr[1], i32), _p(self.csr[2], f), _p(self.falloff, f),
-            _p(self.filt.view(np.float32), f), int(backward), int(mask))
+            _p(self.filt.view(np.float32), f),
+            _p(self.filt_plane.view(np.float32), f) if (fused and self.filt_plane is not None) else None,
+            int(backward), int(mask))
         assert rc == 0, rc
         return out, s1, s2

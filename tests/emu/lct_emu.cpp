@@ -68,7 +68,7 @@ void lct_emu_init(int reverse_threads) {
 int lct_emu_run(int M, int N, int C, int D, int Tin, int be_uniform, const int* be,
                 const float* in, float* out, float* s1, float* s2,
                 const int* mtx_rowptr, const int* mtx_colidx, const float* mtx_vals, const float* falloff,
-                const float* filt, int backward, int mask) {
+                const float* filt, const float* filt_plane, int backward, int mask) {
     lct::HostTables ht;
     if (!lct::build_tables(M, mtx_rowptr, mtx_colidx, mtx_vals, falloff, ht).empty()) return 100;
     auto band = [](const std::vector<lct::EllRow>& e, const std::vector<int32_t>& rp, const std::vector<float>& v) {
@@ -76,10 +76,17 @@ int lct_emu_run(int M, int N, int C, int D, int Tin, int be_uniform, const int* 
     };
     lct::ChainTables t{band(ht.mtx_ell_falloff, ht.mtx_rowptr, ht.mtx_vals_falloff), band(ht.mtx_ell, ht.mtx_rowptr, ht.mtx_vals),
                        band(ht.mtxi_ell, ht.mtxi_rowptr, ht.mtxi_vals), band(ht.mtxi_ell_falloff, ht.mtxi_rowptr, ht.mtxi_vals_falloff),
-                       reinterpret_cast<const float2*>(filt)};
+                       reinterpret_cast<const float2*>(filt), reinterpret_cast<const float2*>(filt_plane)};
     EmuLauncher l;
     return lct::run_chain(l, t, M, N, C, D, Tin, be_uniform, be, 0, in, out,
                           reinterpret_cast<float2*>(s1), reinterpret_cast<float2*>(s2), backward != 0, mask);
+}
+
+// plane row -> H frequency map used to lay out the fused filter (same function lct_api.cu uses)
+int lct_emu_plane_row_freq(int N, int r) {
+    int rc = -1;
+    LCT_SWITCH_N(N, (lct::plane_row_freq<kN>(r)));
+    return rc;
 }
 
 }  // extern "C"
