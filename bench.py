@@ -166,6 +166,7 @@ def main():
 
     import torch.distributed as dist
     import hiddenpose_b200 as hp
+    from hiddenpose_b200 import sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
@@ -211,10 +212,7 @@ def main():
         clocks = sampler.stop()
     step_ms = [ev[0].elapsed_time(ev[5]) for ev in stage_events]
     stage_ms = [[ev[j].elapsed_time(ev[j + 1]) for ev in stage_events] for j in range(5)]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
+    total_ms = sharding.max_over_ranks(sum(step_ms), dev)
     value = world * B * K / (total_ms * 1e-3)
 
     # ---- forward + backward (autograd through the module), device-resident -----------------
@@ -232,10 +230,7 @@ def main():
         fb_events[i][1].record()
         xg.grad = None
     barrier()
-    fb_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in fb_events)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(fb_ms, op=dist.ReduceOp.MAX)
-    fb_ms = float(fb_ms.item())
+    fb_ms = sharding.max_over_ranks(sum(a.elapsed_time(b) for a, b in fb_events), dev)
 
     # ---- end to end: pinned host input -> H2D -> forward -> D2H of the volume, every step ---
     x_host = x.cpu().pin_memory()
@@ -253,10 +248,8 @@ def main():
             y_host.copy_(layer(xd, tbes, tens), non_blocking=True)
         e2e_ev[1].record()
         barrier()
-    e2e_ms = torch.tensor([e2e_ev[0].elapsed_time(e2e_ev[1])], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * K / (float(e2e_ms.item()) * 1e-3)
+    e2e_ms = sharding.max_over_ranks(e2e_ev[0].elapsed_time(e2e_ev[1]), dev)
+    e2e_value = world * B * K / (e2e_ms * 1e-3)
 
     if rank == 0:
         peak, peak_src = measured_peak()
