@@ -8,7 +8,8 @@ hand-written CUDA library behind ``include/hiddenpose_lct.h``.
 from ._native import build_native, load as load_native          # noqa: F401
 from .feature_propagation import LCT, FeaturePropagation, VisibleNet, normalize, normalize_feature   # noqa: F401
 from .lct_function import LctFunction, LctPlan                   # noqa: F401
+from .streaming import LctStreamer                               # noqa: F401
 from .tflct import lct                                           # noqa: F401
 
 __all__ = ["lct", "LCT", "FeaturePropagation", "VisibleNet", "normalize", "normalize_feature",
-           "LctFunction", "LctPlan", "build_native", "load_native"]
+           "LctFunction", "LctPlan", "LctStreamer", "build_native", "load_native"]

@@ -33,8 +33,16 @@ namespace lct {
 constexpr int kTwN = 1024;   // size of the master twiddle table exp(-2*pi*i*j/1024)
 
 // ---- complex helpers -------------------------------------------------------
+// Blackwell packs two fp32 operations into one issue slot (FADD2 / FFMA2, sm_100 only): a complex
+// add or subtract is one instruction instead of two.  The butterflies are adder networks, and the
+// kernels are bound by instruction issue, not by DRAM, so this is where the slots are saved.
+#if !defined(LCT_EMULATE) && !defined(LCT_NO_PACKED_FP32)
+LCT_DEV float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+LCT_DEV float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+#else
 LCT_DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 LCT_DEV float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 LCT_DEV float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 // a * conj(b)
 LCT_DEV float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }

@@ -39,6 +39,19 @@ struct TwGlobal { static LCT_DEV float2 get(int i) { return __ldg(&g_tw[i]); } }
 #define LCT_LDG(p) __ldg(p)
 #endif
 
+// Line-thread index shared by a whole warp (column tiles are multiples of 32 wide): broadcasting it
+// from lane 0 tells the compiler it is warp-uniform, so twiddle-table lookups indexed by it become
+// uniform constant loads held in uniform registers instead of per-thread LDC + vector registers.
+#ifdef LCT_EMULATE
+static inline int warp_uniform(int v) { return v; }
+#else
+LCT_DEV int warp_uniform(int v) { return __reduce_max_sync(0xffffffffu, v); }   // REDUX writes a uniform register
+#endif
+template <int LANES> LCT_DEV int line_thread(int tid) {
+    if constexpr (LANES % 32 == 0) return warp_uniform(tid / LANES);
+    else return tid / LANES;
+}
+
 struct Params {
     int M, N, C, D;
     // K1 input placement: rows [in_be, in_be+in_T) of the M-bin time axis come from `in`
@@ -105,7 +118,7 @@ template <class P, int CT_> struct TimeFwd {
     static int iterations(const Params&) { return 1; }
 
     template <int PH> static LCT_DEV void phase(const Params& p, Regs& r, unsigned char* smem, int tid, int bx, int by, int) {
-        const int col = tid % CT, tau = tid / CT;
+        const int col = tid % CT, tau = line_thread<CT>(tid);
         const int NN = p.N * p.N, col0 = bx * CT, c = by;
         float* xs = reinterpret_cast<float*>(smem);
         float2* zs = reinterpret_cast<float2*>(smem);
@@ -170,7 +183,7 @@ template <class P, int CT_> struct TimeInv {
     static int iterations(const Params&) { return 1; }
 
     template <int PH> static LCT_DEV void phase(const Params& p, Regs& r, unsigned char* smem, int tid, int bx, int by, int) {
-        const int col = tid % CT, tau = tid / CT;
+        const int col = tid % CT, tau = line_thread<CT>(tid);
         const int NN = p.N * p.N, col0 = bx * CT, c = by;
         float2* zs = reinterpret_cast<float2*>(smem);
         float* vol = reinterpret_cast<float*>(smem);
@@ -255,7 +268,7 @@ template <class P, int CT_> struct RowFwd {
     static int iterations(const Params&) { return 1; }
 
     template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem, int tid, int bx, int by, int) {
-        const int col = tid % CT, tau = tid / CT;
+        const int col = tid % CT, tau = line_thread<CT>(tid);
         float2* zs = reinterpret_cast<float2*>(smem);
         const float2* src = p.s1 + (size_t)by * N * N + bx * CT + col;
         float2* dst = p.s2 + (size_t)by * L * N + bx * CT + col;
@@ -289,7 +302,7 @@ template <class P, int CT_> struct RowInv {
     static int iterations(const Params&) { return 1; }
 
     template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem, int tid, int bx, int by, int) {
-        const int col = tid % CT, tau = tid / CT;
+        const int col = tid % CT, tau = line_thread<CT>(tid);
         float2* zs = reinterpret_cast<float2*>(smem);
         const float2* src = p.s2 + (size_t)by * L * N + bx * CT + col;
         float2* dst = p.s1 + (size_t)by * N * N + bx * CT + col;
@@ -430,7 +443,7 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
         constexpr int kW0 = 2, kW1 = 2 + 6 * nWB;
         if constexpr (PH < kW0) {
             // H forward; column batches touch disjoint columns, so they share a phase
-            const int tau = tid / CB;
+            const int tau = line_thread<CB>(tid);
             LCT_UNROLL
             for (int hb = 0; hb < nHB; ++hb) {
                 const int col = hb * CB + tid % CB;
@@ -447,7 +460,7 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
             }
         } else if constexpr (PH < kW1) {
             constexpr int wb = (PH - kW0) / 6, step = (PH - kW0) % 6, par = step / 3, st3 = step % 3;
-            const int rl = tid % RBt, tau = tid / RBt, row = wb * RBt + rl;
+            const int rl = tid % RBt, tau = line_thread<RBt>(tid), row = wb * RBt + rl;
             const bool active = tid < RBt * PWp::TL;
             float2* Tr = T + row * RS;
             if (active) {
@@ -480,7 +493,7 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
             }
         } else {
             constexpr int s = PH - kW1;
-            const int tau = tid / CB;
+            const int tau = line_thread<CB>(tid);
             LCT_UNROLL
             for (int hb = 0; hb < nHB; ++hb) {
                 const int col = hb * CB + tid % CB;

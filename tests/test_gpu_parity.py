@@ -175,3 +175,15 @@ def test_error_behaviour():
         layer(x.cpu(), [0], [M])                                          # no CPU fallback
     with pytest.raises(IndexError):
         layer(torch.zeros(3, 1, M - 1, N, N, device="cuda"), [0, 1], [M - 1, M])
+
+
+def test_streamer_matches_batch_by_batch():
+    """LctStreamer (overlapped upload / transform / download) returns exactly what the layer returns."""
+    import hiddenpose_b200 as hp
+    M, N, B = 64, 16, 2
+    layer = _layer(N, M, 0.08, 1)
+    xs = [torch.rand(B, 1, M, N, N).pin_memory() for _ in range(5)]
+    ys = [torch.empty(B, 1, M, N, N).pin_memory() for _ in range(5)]
+    hp.LctStreamer(layer, [0] * B, [M] * B, depth=2).run(xs, ys)
+    for xh, yh in zip(xs, ys):
+        assert torch.equal(yh, layer(xh.cuda(), [0] * B, [M] * B).cpu())
