@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -14,6 +15,10 @@
 #include "lct_chain.cuh"
 #include "lct_stencil.cuh"
 #include "lct_tables.h"
+
+#ifndef LCT_DEFAULT_STREAM_GROUPS
+#define LCT_DEFAULT_STREAM_GROUPS 2
+#endif
 
 namespace {
 
@@ -124,6 +129,13 @@ struct DeviceBand {
 struct lct_plan {
     int M = 0, N = 0, device = 0;
     DeviceBand mtx_falloff, mtx, mtxi, mtxi_falloff;
+    // Channel groups run as independent kernel chains on side streams, so the tail of one group's
+    // kernel overlaps the next kernel of another group (the chains differ in what bounds them).
+    static constexpr int kMaxGroups = 8;
+    int groups = 1;
+    cudaStream_t side[kMaxGroups] = {};
+    cudaEvent_t fork = nullptr, join[kMaxGroups] = {};
+    mutable std::mutex side_mutex;          // the side streams/events are shared by all callers of the plan
     float2* filt = nullptr;         // natural layout (unfused K3), or
     float2* filt_plane = nullptr;   // [kt][kw][plane row] (plane-fused kernel); exactly one of the two is set
     bool fused() const { return filt_plane != nullptr; }
@@ -170,6 +182,11 @@ void lct_plan_destroy(lct_plan* plan) {
     plan->mtx_falloff.release(); plan->mtx.release(); plan->mtxi.release(); plan->mtxi_falloff.release();
     cudaFree(plan->filt);
     cudaFree(plan->filt_plane);
+    for (int g = 0; g < lct_plan::kMaxGroups; ++g) {
+        if (plan->side[g]) cudaStreamDestroy(plan->side[g]);
+        if (plan->join[g]) cudaEventDestroy(plan->join[g]);
+    }
+    if (plan->fork) cudaEventDestroy(plan->fork);
     delete plan;
 }
 
@@ -222,6 +239,22 @@ int lct_plan_create(const lct_desc* d, lct_plan** out) {
         dev_filt = p->filt;
     }
 #undef LCT_TRY
+    {
+        const char* env = std::getenv("LCT_STREAM_GROUPS");
+        int g = env ? std::atoi(env) : LCT_DEFAULT_STREAM_GROUPS;
+        p->groups = g < 1 ? 1 : (g > lct_plan::kMaxGroups ? lct_plan::kMaxGroups : g);
+        for (int i = 1; i < p->groups; ++i) {
+            if (cudaStreamCreateWithFlags(&p->side[i], cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->join[i], cudaEventDisableTiming) != cudaSuccess) {
+                lct_plan_destroy(p);
+                return fail(LCT_ERR_CUDA, "side stream creation");
+            }
+        }
+        if (p->groups > 1 && cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming) != cudaSuccess) {
+            lct_plan_destroy(p);
+            return fail(LCT_ERR_CUDA, "fork event creation");
+        }
+    }
     // fold torch.ifft's 1/(2M*2N*2N) (tflct.py:151) into the filter; a power of two, so exact
     scale_filter_kernel<<<1024, 256>>>(dev_filt, nfilt, 1.0f / (8.0f * (float)M * (float)N * (float)N));
     cudaError_t e = cudaDeviceSynchronize();
@@ -273,9 +306,29 @@ static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const 
     const size_t in_stride = (size_t)(backward ? M : Tin) * N * N;
     const size_t out_stride = (size_t)(backward ? Tin : M) * N * N;
     if (events && chunk < C) return fail(LCT_ERR_WORKSPACE, "stage events need a workspace for the whole batch");
+    const lct::ChainTables t = plan->tables();
+    if (plan->groups > 1 && chunk >= C && C >= 2 && !events) {     // per-kernel events need the single-stream order
+        // one batch: split the channels into groups, each an independent chain on its own stream
+        std::lock_guard<std::mutex> lock(plan->side_mutex);
+        const int G = (int)(C < plan->groups ? C : plan->groups);
+        LCT_CUDA(cudaEventRecord(plan->fork, stream));
+        for (int g = 0; g < G; ++g) {
+            const long long c0 = C * g / G, c1 = C * (g + 1) / G;
+            cudaStream_t sg = g == 0 ? stream : plan->side[g];
+            if (g) LCT_CUDA(cudaStreamWaitEvent(sg, plan->fork, 0));
+            GpuLauncher lg{sg, plan->device};
+            const int rc = lct::run_chain(lg, t, M, N, (int)(c1 - c0), D, Tin, tbe[0], be_dev, (int)c0,
+                                          in + (size_t)c0 * in_stride, out + (size_t)c0 * out_stride,
+                                          s1 + (size_t)c0 * (M + 1) * N * N, s2 + (size_t)c0 * (M + 1) * 2 * N * N, backward);
+            if (rc < 0) return fail(LCT_ERR_UNSUPPORTED, "size not compiled");
+            if (rc) return fail(LCT_ERR_CUDA, "kernel launch", lg.err);
+            if (g) LCT_CUDA(cudaEventRecord(plan->join[g], sg));
+        }
+        for (int g = 1; g < G; ++g) LCT_CUDA(cudaStreamWaitEvent(stream, plan->join[g], 0));
+        return LCT_OK;
+    }
     GpuLauncher l{stream, plan->device};
     l.events = events;
-    const lct::ChainTables t = plan->tables();
     for (long long c0 = 0; c0 < C; c0 += chunk) {
         const int cn = (int)((C - c0 < chunk) ? (C - c0) : chunk);
         const int rc = lct::run_chain(l, t, M, N, cn, D, Tin, tbe[0], be_dev, (int)c0,

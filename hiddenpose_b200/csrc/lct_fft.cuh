@@ -33,21 +33,31 @@ namespace lct {
 constexpr int kTwN = 1024;   // size of the master twiddle table exp(-2*pi*i*j/1024)
 
 // ---- complex helpers -------------------------------------------------------
-// Blackwell packs two fp32 operations into one issue slot (FADD2 / FFMA2, sm_100 only): a complex
-// add or subtract is one instruction instead of two.  The butterflies are adder networks, and the
-// kernels are bound by instruction issue, not by DRAM, so this is where the slots are saved.
+// Blackwell packs two fp32 operations into one issue slot (FADD2 / FMUL2 / FFMA2, sm_100 only), with
+// free operand swizzles (scalar broadcast, lo/hi swap).  A complex add or subtract is one instruction
+// instead of two, a complex multiply three instead of four.  The kernels are bound by instruction
+// issue inside the SM, not by DRAM, so this is where the slots are saved.
 #if !defined(LCT_EMULATE) && !defined(LCT_NO_PACKED_FP32)
+#define LCT_PACKED_FP32 1
 LCT_DEV float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
 LCT_DEV float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+LCT_DEV float2 cmul(float2 a, float2 b) {
+    return __ffma2_rn(make_float2(a.x, a.x), b, __fmul2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x)));
+}
+// a * conj(b)
+LCT_DEV float2 cmulc(float2 a, float2 b) {
+    return __ffma2_rn(make_float2(a.x, a.x), make_float2(b.x, -b.y), __fmul2_rn(make_float2(a.y, a.y), make_float2(b.y, b.x)));
+}
+LCT_DEV float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
 #else
 LCT_DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 LCT_DEV float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-#endif
 LCT_DEV float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 // a * conj(b)
 LCT_DEV float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
-LCT_DEV float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 LCT_DEV float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+#endif
+LCT_DEV float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 // multiply by -i (forward) / +i (inverse)
 template <bool INV> LCT_DEV float2 mul_mi(float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
 
@@ -83,16 +93,25 @@ template <bool INV> LCT_DEV float2 twmul32(float2 a, int idx) {
     else if (quad == 2) { cc = -c; ss = -s; }
     else { cc = s; ss = -c; }
     // forward: multiply by (cc - i ss); inverse: (cc + i ss)
-    if (r == 4) {   // |cc| == |ss| == 1/sqrt2 : 2 adds + 2 muls
+    if (r == 4) {   // |cc| == |ss| == 1/sqrt2 : one add network + one scale
         const float h = 0.70710678118654752f;
         const float sx = (cc > 0.f) ? 1.f : -1.f, sy = (ss > 0.f) ? 1.f : -1.f;
         // (x + i y) * (sx - i*sgn*sy) * h, sgn = +1 forward
         const float sg = INV ? -sy : sy;
         // real: sx*x + sg*y ; imag: sx*y - sg*x
+#ifdef LCT_PACKED_FP32
+        return __fmul2_rn(__fadd2_rn(make_float2(sx * a.x, sx * a.y), make_float2(sg * a.y, -sg * a.x)), make_float2(h, h));
+#else
         return make_float2(h * (sx * a.x + sg * a.y), h * (sx * a.y - sg * a.x));
+#endif
     }
     if (INV) ss = -ss;
+#ifdef LCT_PACKED_FP32
+    // (x*cc + y*ss, y*cc - x*ss) = x*(cc, -ss) + y*(ss, cc)
+    return __ffma2_rn(make_float2(a.x, a.x), make_float2(cc, -ss), __fmul2_rn(make_float2(a.y, a.y), make_float2(ss, cc)));
+#else
     return make_float2(a.x * cc + a.y * ss, a.y * cc - a.x * ss);
+#endif
 }
 
 // ---- in-register DFTs, natural-order output -------------------------------
@@ -184,17 +203,21 @@ template <int R0_, int R1_, int R2_ = 1> struct Plan {
     static constexpr int radix(int s) { return s == 0 ? R0 : (s == 1 ? R1 : R2); }
     static constexpr int Ls(int s) { return s == 0 ? L : (s == 1 ? L / R0 : L / (R0 * R1)); }
     static constexpr int st(int s) { return Ls(s) / radix(s); }
+    static constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v / 2); }
+    static constexpr int B0 = ilog2(R0), B1 = ilog2(R1), B2 = ilog2(R2);
+    // positions and frequencies are the same digits in opposite order; all radices are powers of two,
+    // so both maps are bit-field permutations (linear over disjoint bit sets)
     LCT_HD static int pos_to_freq(int p) {
-        int f = p / st(0);                       // k0
-        if (S > 1) f += R0 * ((p / st(1)) % R1);
-        if (S > 2) f += R0 * R1 * (p % R2);
-        return f;
+        return (p >> (B1 + B2)) | (((p >> B2) & (R1 - 1)) << B0) | ((p & (R2 - 1)) << (B0 + B1));
     }
     LCT_HD static int freq_to_pos(int f) {
-        int p = (f % R0) * st(0);
-        if (S > 1) p += ((f / R0) % R1) * st(1);
-        if (S > 2) p += (f / (R0 * R1));
-        return p;
+        return ((f & (R0 - 1)) << (B1 + B2)) | (((f >> B0) & (R1 - 1)) << B2) | (f >> (B0 + B1));
+    }
+    // frequency of the element a stage-s thread addresses as (pos, slot): the butterfly base is mapped
+    // once at run time, the element's own digit (slot % radix, known at compile time) is a constant
+    template <int s> LCT_HD static int freq_of(int pos, int slot) {
+        const int off = (slot % radix(s)) * st(s);
+        return pos_to_freq(pos - off) + pos_to_freq(off);
     }
 };
 

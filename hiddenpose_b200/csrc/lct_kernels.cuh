@@ -154,17 +154,31 @@ template <class P, int CT_> struct TimeFwd {
                 [&](int pos, int) { return zs[pos * CT + col]; },
                 [&](int pos, int, float2 v) { zs[pos * CT + col] = v; });
         } else {
+            // X[k] = Ev + w^k Od and X[M-k] = conj(Ev - w^k Od) from the pair (Z[k], Z[M-k])
             float2* dst = p.s1 + (size_t)c * (M + 1) * NN + col0 + col;
-            for (int k = tau; k <= M / 2; k += P::TL) {
-                const float2 zk = zs[P::freq_to_pos(k) * CT + col];
-                const float2 zm = cconj(zs[P::freq_to_pos((M - k) % M) * CT + col]);
+            const float2* zc = zs + col;
+            auto emit = [&](int k, int pos_k, float2* lo, float2* hi) {
+                const float2 zk = zc[pos_k * CT];
+                const float2 zm = cconj(zc[P::freq_to_pos((M - k) & (M - 1)) * CT]);
                 const float2 ev = cscale(cadd(zk, zm), 0.5f);
                 const float2 d = csub(zk, zm);
                 const float2 od = make_float2(0.5f * d.y, -0.5f * d.x);
                 const float2 t = cmul(od, TwConst::get(k * (kTwN / (2 * M))));
-                dst[(size_t)k * NN] = cadd(ev, t);
-                if (k != M - k) dst[(size_t)(M - k) * NN] = cconj(csub(ev, t));
+                *lo = cadd(ev, t);
+                if (hi != lo) *hi = cconj(csub(ev, t));
+            };
+            constexpr int kPairs = (M / 2) / P::TL;                  // k = tau + m*TL < M/2
+            float2* lo = dst + (size_t)tau * NN;
+            float2* hi = dst + (size_t)(M - tau) * NN;
+            const size_t step = (size_t)P::TL * NN;
+            const int pos_tau = P::freq_to_pos(tau);
+            LCT_UNROLL
+            for (int m = 0; m < kPairs; ++m) {
+                emit(tau + m * P::TL, pos_tau + P::freq_to_pos(m * P::TL), lo, hi);   // disjoint bit fields
+                lo += step;
+                hi -= step;
             }
+            if (tau == 0) emit(M / 2, P::freq_to_pos(M / 2), dst + (size_t)(M / 2) * NN, dst + (size_t)(M / 2) * NN);
         }
     }
 };
@@ -214,11 +228,11 @@ template <class P, int CT_> struct TimeInv {
             };
             if constexpr (SL == 0) {
                 inv_stage<P, 0, true, TwConst>(tau,
-                    [&](int pos, int) { return z_at(P::pos_to_freq(pos)); },
+                    [&](int pos, int slot) { return z_at(P::template freq_of<0>(pos, slot)); },
                     [&](int, int slot, float2 v) { r.a[slot] = v; });
             } else {
                 inv_stage<P, SL, false, TwConst>(tau,
-                    [&](int pos, int) { return z_at(P::pos_to_freq(pos)); },
+                    [&](int pos, int slot) { return z_at(P::template freq_of<SL>(pos, slot)); },
                     [&](int, int slot, float2 v) { r.a[slot] = v; });
             }
         } else if constexpr (PH == 2) {
@@ -249,7 +263,13 @@ template <class P, int CT_> struct TimeInv {
         } else if constexpr (PH == kPhases - 1) {
             const int be = window_begin(p, c);
             float* dst = p.out + (size_t)c * p.out_T * NN + col0 + col;
-            for (int j = tau; j < p.out_T; j += P::TL) dst[(size_t)j * NN] = band_dot(p, be + j, vol + col, CT);
+            float* d = dst + (size_t)tau * NN;
+            const size_t step = (size_t)P::TL * NN;
+            const float* vc = vol + col;
+#ifndef LCT_EMULATE
+#pragma unroll 4
+#endif
+            for (int j = tau; j < p.out_T; j += P::TL, d += step) *d = band_dot(p, be + j, vc, CT);
         }
     }
 };
@@ -275,7 +295,7 @@ template <class P, int CT_> struct RowFwd {
         auto ld_g = [&](int pos, int) { return src[(size_t)pos * N]; };
         auto ld_s = [&](int pos, int) { return zs[pos * CT + col]; };
         auto st_s = [&](int pos, int, float2 v) { zs[pos * CT + col] = v; };
-        auto st_g = [&](int pos, int, float2 v) { dst[(size_t)P::pos_to_freq(pos) * N] = v; };
+        auto st_g = [&](int pos, int slot, float2 v) { dst[(size_t)P::template freq_of<P::S - 1>(pos, slot) * N] = v; };
         if constexpr (P::S == 1) {
             fwd_stage<P, 0, true, TwConst>(tau, ld_g, st_g);
         } else if constexpr (PH == 0) {
@@ -306,7 +326,7 @@ template <class P, int CT_> struct RowInv {
         float2* zs = reinterpret_cast<float2*>(smem);
         const float2* src = p.s2 + (size_t)by * L * N + bx * CT + col;
         float2* dst = p.s1 + (size_t)by * N * N + bx * CT + col;
-        auto ld_g = [&](int pos, int) { return src[(size_t)P::pos_to_freq(pos) * N]; };
+        auto ld_g = [&](int pos, int slot) { return src[(size_t)P::template freq_of<P::S - 1>(pos, slot) * N]; };
         auto ld_s = [&](int pos, int) { return zs[pos * CT + col]; };
         auto st_s = [&](int pos, int, float2 v) { zs[pos * CT + col] = v; };
         auto st_g = [&](int pos, int, float2 v) { dst[(size_t)pos * N] = v; };
@@ -368,7 +388,7 @@ template <class P, int RB_> struct ColFilter {
                 fetch(row, tau, r);
                 const float2* f = p.filt + ((size_t)kt * L + kh) * L;
                 for_each_slot<P, 1>(tau, [&](int pos, int slot) {
-                    float2 w = LCT_LDG(f + P::pos_to_freq(pos));
+                    float2 w = LCT_LDG(f + P::template freq_of<1>(pos, slot));
                     if (p.conj_filter) w.y = -w.y;
                     r.w[slot] = w;
                 });
@@ -402,8 +422,8 @@ template <class P, int RB_> struct ColFilter {
 //   H forward  : K2's stages, lanes along W, output rows stay in plan position order.
 //   W pass     : per row, the 2N-point zero-extended FFT is two N-point FFTs (even / odd
 //                output frequencies, the odd one pre-rotated by w_2N^n); each is filtered and
-//                inverted in place in the row's own N slots, the two results recombined
-//                (y = y_even + conj(w_2N^n) y_odd).  Lanes run along H here, so twiddles are
+//                inverted -- the even one in the row's own N slots, the odd one in a 1-batch side
+//                buffer -- and the two results recombined (y = y_even + conj(w_2N^n) y_odd).  Lanes run along H here, so twiddles are
 //                warp-uniform constant-bank reads and the filter, stored as [kt][kw][row], is
 //                read coalesced.
 //   H inverse  : K4's stages, written back over the input plane in S1.
@@ -419,28 +439,26 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
     static_assert(L % RBt == 0, "row batches must tile the plane");
     static constexpr int nWB = L / RBt;
     static constexpr int RS = N + 1;
-    static constexpr size_t kSmem = (size_t)L * RS * sizeof(float2);
-    static constexpr int kPhases = 2 + nWB * 6 + 2;
+    // plane T[L][RS] + side buffer X[RBt][RS]: the odd-parity transform of a row batch is exchanged
+    // through X while the even one uses the rows' own slots, so both run in the same three phases
+    static constexpr size_t kSmem = (size_t)(L + RBt) * RS * sizeof(float2);
+    static constexpr int kPhases = 2 + nWB * 3 + 2;
     static constexpr int EW = PWp::E;
     static constexpr bool kWarpSync = false;
 #ifndef LCT_PLANE_MINBLOCKS
 #define LCT_PLANE_MINBLOCKS 2
 #endif
     static constexpr int kMinBlocks = (LCT_PLANE_MINBLOCKS * kSmem <= 220 * 1024) ? LCT_PLANE_MINBLOCKS : 1;
-    struct Regs { float2 in[EW]; float2 acc[EW]; };
+    struct Regs {};
     static void grid(const Params& p, int& gx, int& gy) { gx = p.C; gy = p.M + 1; }   // c fastest: filter plane reused from L2
     static int iterations(const Params&) { return 1; }
 
-    // address of the filter value a W-pass thread needs for (plane row, N-point position, parity)
-    static LCT_DEV const float2* filt_at(const Params& p, int kt, int row, int pos, int par) {
-        return p.filt + ((size_t)kt * L + (2 * PWp::pos_to_freq(pos) + par)) * L + row;        // [kt][kw][row]
-    }
-
-    template <int PH> static LCT_DEV void phase(const Params& p, Regs& r, unsigned char* smem, int tid, int bx, int by, int) {
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem, int tid, int bx, int by, int) {
         float2* T = reinterpret_cast<float2*>(smem);
+        float2* X = T + L * RS;
         const int kt = by;
         const size_t plane = (size_t)bx * (p.M + 1) + kt;
-        constexpr int kW0 = 2, kW1 = 2 + 6 * nWB;
+        constexpr int kW0 = 2, kW1 = 2 + 3 * nWB;
         if constexpr (PH < kW0) {
             // H forward; column batches touch disjoint columns, so they share a phase
             const int tau = line_thread<CB>(tid);
@@ -459,37 +477,62 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
                 }
             }
         } else if constexpr (PH < kW1) {
-            constexpr int wb = (PH - kW0) / 6, step = (PH - kW0) % 6, par = step / 3, st3 = step % 3;
+            // W pass of one row batch: even (a) and odd (b) output parities side by side
+            constexpr int wb = (PH - kW0) / 3, st3 = (PH - kW0) % 3;
             const int rl = tid % RBt, tau = line_thread<RBt>(tid), row = wb * RBt + rl;
-            const bool active = tid < RBt * PWp::TL;
+            if (tid >= RBt * PWp::TL) return;
             float2* Tr = T + row * RS;
-            if (active) {
-                if constexpr (st3 == 0) {
-                    if constexpr (par == 0) {
-                        for_each_slot<PWp, 0>(tau, [&](int pos, int slot) { r.in[slot] = Tr[pos]; });
-                    }
-                    fwd_stage<PWp, 0, false, TwConst>(tau,
-                        [&](int pos, int slot) {
-                            return par == 0 ? r.in[slot] : cmul(r.in[slot], TwConst::get(pos * (kTwN / L)));
-                        },
-                        [&](int pos, int, float2 v) { Tr[pos] = v; });
-                } else if constexpr (st3 == 1) {
-                    float2 w[EW], b[EW];
-                    for_each_slot<PWp, 1>(tau, [&](int pos, int slot) { w[slot] = LCT_LDG(filt_at(p, kt, row, pos, par)); });
-                    fwd_stage<PWp, 1, false, TwConst>(tau,
-                        [&](int pos, int) { return Tr[pos]; },
-                        [&](int, int slot, float2 v) { b[slot] = p.conj_filter ? cmulc(v, w[slot]) : cmul(v, w[slot]); });
-                    inv_stage<PWp, 1, false, TwConst>(tau,
-                        [&](int, int slot) { return b[slot]; },
-                        [&](int pos, int, float2 v) { Tr[pos] = v; });
-                } else {
-                    inv_stage<PWp, 0, false, TwConst>(tau,
-                        [&](int pos, int) { return Tr[pos]; },
-                        [&](int pos, int slot, float2 v) {
-                            if constexpr (par == 0) r.acc[slot] = v;
-                            else Tr[pos] = cadd(r.acc[slot], cmulc(v, TwConst::get(pos * (kTwN / L))));
-                        });
+            float2* Xr = X + rl * RS;
+            if constexpr (st3 == 0) {
+                float2 in[EW];
+                for_each_slot<PWp, 0>(tau, [&](int pos, int slot) { in[slot] = Tr[pos]; });
+                fwd_stage<PWp, 0, false, TwConst>(tau,
+                    [&](int, int slot) { return in[slot]; },
+                    [&](int pos, int, float2 v) { Tr[pos] = v; });
+                fwd_stage<PWp, 0, false, TwConst>(tau,
+                    [&](int pos, int slot) { return cmul(in[slot], TwConst::get(pos * (kTwN / L))); },
+                    [&](int pos, int, float2 v) { Xr[pos] = v; });
+#if !defined(LCT_EMULATE) && defined(LCT_PLANE_PREFETCH)
+                {   // pull next phase's filter values from L2 towards L1 while the exchange settles
+                    const float2* f = p.filt + (size_t)kt * L * L + row;
+                    for_each_slot<PWp, 1>(tau, [&](int pos, int) {
+                        const float2* q = f + (size_t)(2 * PWp::pos_to_freq(pos)) * L;
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(q + L));
+                    });
                 }
+#endif
+            } else if constexpr (st3 == 1) {
+                const float2* f = p.filt + (size_t)kt * L * L + row;          // [kt][kw][row]
+                float2 wa[EW], wb_[EW];
+                for_each_slot<PWp, 1>(tau, [&](int pos, int slot) {
+                    const float2* q = f + (size_t)(2 * PWp::template freq_of<1>(pos, slot)) * L;
+                    wa[slot] = LCT_LDG(q);
+                    wb_[slot] = LCT_LDG(q + L);
+                });
+                float2 b[EW];
+                fwd_stage<PWp, 1, false, TwConst>(tau,
+                    [&](int pos, int) { return Tr[pos]; },
+                    [&](int, int slot, float2 v) { b[slot] = p.conj_filter ? cmulc(v, wa[slot]) : cmul(v, wa[slot]); });
+                inv_stage<PWp, 1, false, TwConst>(tau,
+                    [&](int, int slot) { return b[slot]; },
+                    [&](int pos, int, float2 v) { Tr[pos] = v; });
+                fwd_stage<PWp, 1, false, TwConst>(tau,
+                    [&](int pos, int) { return Xr[pos]; },
+                    [&](int, int slot, float2 v) { b[slot] = p.conj_filter ? cmulc(v, wb_[slot]) : cmul(v, wb_[slot]); });
+                inv_stage<PWp, 1, false, TwConst>(tau,
+                    [&](int, int slot) { return b[slot]; },
+                    [&](int pos, int, float2 v) { Xr[pos] = v; });
+            } else {
+                float2 ya[EW];
+                inv_stage<PWp, 0, false, TwConst>(tau,
+                    [&](int pos, int) { return Tr[pos]; },
+                    [&](int, int slot, float2 v) { ya[slot] = v; });
+                inv_stage<PWp, 0, false, TwConst>(tau,
+                    [&](int pos, int) { return Xr[pos]; },
+                    [&](int pos, int slot, float2 v) {
+                        Tr[pos] = cadd(ya[slot], cmulc(v, TwConst::get(pos * (kTwN / L))));
+                    });
             }
         } else {
             constexpr int s = PH - kW1;

@@ -98,7 +98,9 @@ int lct_backward(const lct_plan* plan, const float* gy, const int32_t* tbe, cons
  * Measurement hook: lct_forward (backward == 0) or lct_backward (backward != 0) with six
  * caller-created cudaEvent_t recorded on `stream`: events6[i] before kernel i (time-forward,
  * row-forward, column-filter, row-inverse, time-inverse) and events6[5] after the last one.
- * Needs a workspace for the whole batch.  Same results as the plain calls.
+ * Needs a workspace for the whole batch.  Same results as the plain calls, but the kernels run
+ * back to back on `stream` only (the plain calls split the channels over two internal streams so
+ * that consecutive kernels of different channel groups overlap; set LCT_STREAM_GROUPS=1 to disable).
  */
 int lct_run_staged(const lct_plan* plan, const float* in, const int32_t* tbe, const int32_t* ten,
                    int32_t B, int32_t D, int32_t Tin, float* out,
