@@ -39,6 +39,33 @@ struct TwGlobal { static LCT_DEV float2 get(int i) { return __ldg(&g_tw[i]); } }
 #define LCT_LDG(p) __ldg(p)
 #endif
 
+// Constant-bank twiddles behind the same interface as TwShared (no table, nothing to fill).
+struct TwNone {
+    static constexpr size_t kBytes = 0;
+    static LCT_DEV float2 get(int i) { return TwConst::get(i); }
+    static LCT_DEV void fill(unsigned char*, int, int) {}
+};
+
+// Twiddles from a block-local copy of the table at the very start of dynamic shared memory
+// (entries w_L^j, j < L): a warp-uniform LDS broadcast has a shorter, steadier latency than an
+// indexed constant-bank load, and these loads sit on the critical path of every butterfly.
+template <int L> struct TwShared {
+    static constexpr int kEntries = L;
+    static constexpr size_t kBytes = (size_t)L * sizeof(float2);
+#ifdef LCT_EMULATE
+    static inline float2 get(int i) { return h_tw[i]; }
+    static inline void fill(unsigned char*, int, int) {}
+#else
+    static LCT_DEV float2 get(int i) {
+        extern __shared__ __align__(16) unsigned char lct_dyn_smem[];
+        return reinterpret_cast<const float2*>(lct_dyn_smem)[i / (kTwN / L)];
+    }
+    static LCT_DEV void fill(unsigned char* smem, int tid, int nthreads) {
+        for (int j = tid; j < L; j += nthreads) reinterpret_cast<float2*>(smem)[j] = c_tw[j * (kTwN / L)];
+    }
+#endif
+};
+
 // Line-thread index shared by a whole warp (column tiles are multiples of 32 wide): broadcasting it
 // from lane 0 tells the compiler it is warp-uniform, so twiddle-table lookups indexed by it become
 // uniform constant loads held in uniform registers instead of per-thread LDC + vector registers.
@@ -83,8 +110,8 @@ LCT_DEV int float_bits(float f) { return __float_as_int(f); }
 
 // sum_e w[e] * src[(start + e) * stride] for one operator row; `src` must have two readable
 // (finite) rows past the last one, because short rows still touch three.
-LCT_DEV float band_dot(const Params& p, int row, const float* src, int stride) {
-    const float4 e = LCT_LDG(p.ell + row);
+LCT_DEV float band_dot(const Params& p, const float4* ell, int row, const float* src, int stride) {
+    const float4 e = ell[row];                     // block-local copy in shared memory (warp-uniform: broadcast)
     const int sl = float_bits(e.x), start = sl & 0xffff, len = sl >> 16;
     const float* s = src + start * stride;
     float acc = e.y * s[0];
@@ -107,17 +134,24 @@ LCT_DEV int window_begin(const Params& p, int c) {
 // X[k] = Ev + w^k Od with Ev = (Z[k] + conj Z[M-k])/2, Od = -i (Z[k] - conj Z[M-k])/2.
 // ---------------------------------------------------------------------------
 template <class P, int CT_> struct TimeFwd {
+    using TwS = TwNone;                        // constant-bank twiddles (a block-local table measured slower here)
     static constexpr int M = P::L, CT = CT_, kThreads = P::TL * CT;
     static constexpr int kPhases = 3 + (P::S - 1) + 1;
-    static constexpr size_t kSmem = (size_t)M * CT * sizeof(float2);
-    static_assert((size_t)(M + 2) * CT * sizeof(float) <= kSmem, "x tile must fit");
+    static constexpr size_t kWork = (size_t)M * CT * sizeof(float2);
+    static constexpr size_t kSmem = TwS::kBytes + (kWork + (size_t)M * sizeof(float4));       // + the operator's row records
+    static_assert((size_t)(M + 2) * CT * sizeof(float) <= kWork, "x tile must fit");
+    static_assert(M <= kThreads, "one thread per row record");
     static constexpr bool kWarpSync = false;
     static constexpr int kMinBlocks = (kThreads >= 1024) ? 1 : 1024 / kThreads;     // 1024 threads/SM at <= 64 regs
     struct Regs { float2 a[P::E]; };
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N * p.N / CT; gy = p.C; }
     static int iterations(const Params&) { return 1; }
 
-    template <int PH> static LCT_DEV void phase(const Params& p, Regs& r, unsigned char* smem, int tid, int bx, int by, int) {
+    static constexpr bool kHasPrologue = true;
+    static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwS::fill(smem, tid, kThreads); }
+
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs& r, unsigned char* smem_base, int tid, int bx, int by, int) {
+        unsigned char* smem = smem_base + TwS::kBytes;
         const int col = tid % CT, tau = line_thread<CT>(tid);
         const int NN = p.N * p.N, col0 = bx * CT, c = by;
         float* xs = reinterpret_cast<float*>(smem);
@@ -128,6 +162,7 @@ template <class P, int CT_> struct TimeFwd {
             constexpr int V4 = CT / 4, kSlots = (M + 2) * V4;
             const float4* src = reinterpret_cast<const float4*>(p.in + (size_t)c * p.in_T * NN + col0);
             float4* xs4 = reinterpret_cast<float4*>(smem);
+            if (tid < M) reinterpret_cast<float4*>(smem + kWork)[tid] = LCT_LDG(p.ell + tid);
             float4 v[(kSlots + kThreads - 1) / kThreads];
             LCT_UNROLL
             for (int u = 0; u < (kSlots + kThreads - 1) / kThreads; ++u) {
@@ -141,16 +176,17 @@ template <class P, int CT_> struct TimeFwd {
                 if (i < kSlots) xs4[i] = v[u];
             }
         } else if constexpr (PH == 1) {
-            fwd_stage<P, 0, true, TwConst>(tau,
+            fwd_stage<P, 0, true, TwS>(tau,
                 [&](int pos, int) {
-                    return make_float2(band_dot(p, 2 * pos, xs + col, CT), band_dot(p, 2 * pos + 1, xs + col, CT));
+                    const float4* ell = reinterpret_cast<const float4*>(smem + kWork);
+                    return make_float2(band_dot(p, ell, 2 * pos, xs + col, CT), band_dot(p, ell, 2 * pos + 1, xs + col, CT));
                 },
                 [&](int, int slot, float2 v) { r.a[slot] = v; });
         } else if constexpr (PH == 2) {
             for_each_slot<P, 0>(tau, [&](int pos, int slot) { zs[pos * CT + col] = r.a[slot]; });
         } else if constexpr (PH < 2 + P::S) {
             constexpr int s = PH - 2;
-            fwd_stage<P, s, false, TwConst>(tau,
+            fwd_stage<P, s, false, TwS>(tau,
                 [&](int pos, int) { return zs[pos * CT + col]; },
                 [&](int pos, int, float2 v) { zs[pos * CT + col] = v; });
         } else {
@@ -163,7 +199,7 @@ template <class P, int CT_> struct TimeFwd {
                 const float2 ev = cscale(cadd(zk, zm), 0.5f);
                 const float2 d = csub(zk, zm);
                 const float2 od = make_float2(0.5f * d.y, -0.5f * d.x);
-                const float2 t = cmul(od, TwConst::get(k * (kTwN / (2 * M))));
+                const float2 t = cmul(od, TwS::get(k * (kTwN / (2 * M))));
                 *lo = cadd(ev, t);
                 if (hi != lo) *hi = cconj(csub(ev, t));
             };
@@ -187,16 +223,23 @@ template <class P, int CT_> struct TimeFwd {
 // K5: Hermitian inverse FFT along T (keep t < M), real part, mtxi gather.
 // ---------------------------------------------------------------------------
 template <class P, int CT_> struct TimeInv {
+    using TwS = TwNone;                        // constant-bank twiddles (a block-local table measured slower here)
     static constexpr int M = P::L, CT = CT_, kThreads = P::TL * CT;
     static constexpr int kPhases = 2 + P::S + 2;          // load | stage S-1 -> regs | scatter | middle.. | stage 0 -> regs | scatter vol | gather
-    static constexpr size_t kSmem = (size_t)(M + 1) * CT * sizeof(float2);
+    static constexpr size_t kWork = (size_t)(M + 1) * CT * sizeof(float2);
+    static constexpr size_t kSmem = TwS::kBytes + (kWork + (size_t)M * sizeof(float4));       // + the operator's row records
+    static_assert(M <= kThreads, "one thread per row record");
     static constexpr bool kWarpSync = false;
     static constexpr int kMinBlocks = (kThreads >= 1024) ? 1 : 1024 / kThreads;     // 1024 threads/SM at <= 64 regs
     struct Regs { float2 a[P::E]; };
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N * p.N / CT; gy = p.C; }
     static int iterations(const Params&) { return 1; }
 
-    template <int PH> static LCT_DEV void phase(const Params& p, Regs& r, unsigned char* smem, int tid, int bx, int by, int) {
+    static constexpr bool kHasPrologue = true;
+    static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwS::fill(smem, tid, kThreads); }
+
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs& r, unsigned char* smem_base, int tid, int bx, int by, int) {
+        unsigned char* smem = smem_base + TwS::kBytes;
         const int col = tid % CT, tau = line_thread<CT>(tid);
         const int NN = p.N * p.N, col0 = bx * CT, c = by;
         float2* zs = reinterpret_cast<float2*>(smem);
@@ -207,6 +250,7 @@ template <class P, int CT_> struct TimeInv {
             constexpr int V2 = CT / 2, kSlots = (M + 1) * V2;
             const float4* src = reinterpret_cast<const float4*>(p.s1 + (size_t)c * (M + 1) * NN + col0);
             float4* zs4 = reinterpret_cast<float4*>(smem);
+            if (tid < M) reinterpret_cast<float4*>(smem + kWork)[tid] = LCT_LDG(p.ell + tid);
             float4 v[(kSlots + kThreads - 1) / kThreads];
             LCT_UNROLL
             for (int u = 0; u < (kSlots + kThreads - 1) / kThreads; ++u) {
@@ -223,15 +267,15 @@ template <class P, int CT_> struct TimeInv {
             auto z_at = [&](int k) -> float2 {
                 const float2 xk = zs[k * CT + col];
                 const float2 xm = cconj(zs[(M - k) * CT + col]);
-                const float2 d = cmulc(csub(xk, xm), TwConst::get(k * (kTwN / (2 * M))));
+                const float2 d = cmulc(csub(xk, xm), TwS::get(k * (kTwN / (2 * M))));
                 return cadd(cadd(xk, xm), make_float2(-d.y, d.x));
             };
             if constexpr (SL == 0) {
-                inv_stage<P, 0, true, TwConst>(tau,
+                inv_stage<P, 0, true, TwS>(tau,
                     [&](int pos, int slot) { return z_at(P::template freq_of<0>(pos, slot)); },
                     [&](int, int slot, float2 v) { r.a[slot] = v; });
             } else {
-                inv_stage<P, SL, false, TwConst>(tau,
+                inv_stage<P, SL, false, TwS>(tau,
                     [&](int pos, int slot) { return z_at(P::template freq_of<SL>(pos, slot)); },
                     [&](int, int slot, float2 v) { r.a[slot] = v; });
             }
@@ -247,11 +291,11 @@ template <class P, int CT_> struct TimeInv {
             }
         } else if constexpr (PH < 2 + SL) {          // middle stages SL-1 .. 1, in place
             constexpr int s = SL - (PH - 2);
-            inv_stage<P, s, false, TwConst>(tau,
+            inv_stage<P, s, false, TwS>(tau,
                 [&](int pos, int) { return zs[pos * CT + col]; },
                 [&](int pos, int, float2 v) { zs[pos * CT + col] = v; });
         } else if constexpr (PH == 2 + SL && SL > 0) {
-            inv_stage<P, 0, true, TwConst>(tau,
+            inv_stage<P, 0, true, TwS>(tau,
                 [&](int pos, int) { return zs[pos * CT + col]; },
                 [&](int, int slot, float2 v) { r.a[slot] = v; });
         } else if constexpr (PH == 3 + SL && SL > 0) {
@@ -269,7 +313,8 @@ template <class P, int CT_> struct TimeInv {
 #ifndef LCT_EMULATE
 #pragma unroll 4
 #endif
-            for (int j = tau; j < p.out_T; j += P::TL, d += step) *d = band_dot(p, be + j, vc, CT);
+            const float4* ell = reinterpret_cast<const float4*>(smem + kWork);
+            for (int j = tau; j < p.out_T; j += P::TL, d += step) *d = band_dot(p, ell, be + j, vc, CT);
         }
     }
 };
@@ -278,16 +323,21 @@ template <class P, int CT_> struct TimeInv {
 // K2: zero-extended forward FFT along H.  One block = one (c, kt) plane x CT columns.
 // ---------------------------------------------------------------------------
 template <class P, int CT_> struct RowFwd {
+    using TwS = TwNone;                        // constant-bank twiddles (a block-local table measured slower here)
     static constexpr int L = P::L, N = L / 2, CT = CT_, kThreads = P::TL * CT;
     static constexpr int kPhases = P::S;
     static constexpr bool kWarpSync = false;
     static constexpr int kMinBlocks = (kThreads >= 1024) ? 1 : ((1024 / kThreads) > 32 ? 32 : (1024 / kThreads));   // <= 64 regs
-    static constexpr size_t kSmem = (P::S > 1) ? (size_t)L * CT * sizeof(float2) : 0;
+    static constexpr size_t kSmem = TwS::kBytes + ((P::S > 1) ? (size_t)L * CT * sizeof(float2) : 0);
     struct Regs {};
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N / CT; gy = p.C * (p.M + 1); }
     static int iterations(const Params&) { return 1; }
 
-    template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem, int tid, int bx, int by, int) {
+    static constexpr bool kHasPrologue = true;
+    static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwS::fill(smem, tid, kThreads); }
+
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem_base, int tid, int bx, int by, int) {
+        unsigned char* smem = smem_base + TwS::kBytes;
         const int col = tid % CT, tau = line_thread<CT>(tid);
         float2* zs = reinterpret_cast<float2*>(smem);
         const float2* src = p.s1 + (size_t)by * N * N + bx * CT + col;
@@ -297,13 +347,13 @@ template <class P, int CT_> struct RowFwd {
         auto st_s = [&](int pos, int, float2 v) { zs[pos * CT + col] = v; };
         auto st_g = [&](int pos, int slot, float2 v) { dst[(size_t)P::template freq_of<P::S - 1>(pos, slot) * N] = v; };
         if constexpr (P::S == 1) {
-            fwd_stage<P, 0, true, TwConst>(tau, ld_g, st_g);
+            fwd_stage<P, 0, true, TwS>(tau, ld_g, st_g);
         } else if constexpr (PH == 0) {
-            fwd_stage<P, 0, true, TwConst>(tau, ld_g, st_s);
+            fwd_stage<P, 0, true, TwS>(tau, ld_g, st_s);
         } else if constexpr (PH < P::S - 1) {
-            fwd_stage<P, PH, false, TwConst>(tau, ld_s, st_s);
+            fwd_stage<P, PH, false, TwS>(tau, ld_s, st_s);
         } else {
-            fwd_stage<P, P::S - 1, false, TwConst>(tau, ld_s, st_g);
+            fwd_stage<P, P::S - 1, false, TwS>(tau, ld_s, st_g);
         }
     }
 };
@@ -312,16 +362,21 @@ template <class P, int CT_> struct RowFwd {
 // K4: inverse FFT along H, keep h < N.
 // ---------------------------------------------------------------------------
 template <class P, int CT_> struct RowInv {
+    using TwS = TwNone;                        // constant-bank twiddles (a block-local table measured slower here)
     static constexpr int L = P::L, N = L / 2, CT = CT_, kThreads = P::TL * CT;
     static constexpr int kPhases = P::S;
     static constexpr bool kWarpSync = false;
     static constexpr int kMinBlocks = (kThreads >= 1024) ? 1 : ((1024 / kThreads) > 32 ? 32 : (1024 / kThreads));   // <= 64 regs
-    static constexpr size_t kSmem = (P::S > 1) ? (size_t)L * CT * sizeof(float2) : 0;
+    static constexpr size_t kSmem = TwS::kBytes + ((P::S > 1) ? (size_t)L * CT * sizeof(float2) : 0);
     struct Regs {};
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N / CT; gy = p.C * (p.M + 1); }
     static int iterations(const Params&) { return 1; }
 
-    template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem, int tid, int bx, int by, int) {
+    static constexpr bool kHasPrologue = true;
+    static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwS::fill(smem, tid, kThreads); }
+
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem_base, int tid, int bx, int by, int) {
+        unsigned char* smem = smem_base + TwS::kBytes;
         const int col = tid % CT, tau = line_thread<CT>(tid);
         float2* zs = reinterpret_cast<float2*>(smem);
         const float2* src = p.s2 + (size_t)by * L * N + bx * CT + col;
@@ -331,13 +386,13 @@ template <class P, int CT_> struct RowInv {
         auto st_s = [&](int pos, int, float2 v) { zs[pos * CT + col] = v; };
         auto st_g = [&](int pos, int, float2 v) { dst[(size_t)pos * N] = v; };
         if constexpr (P::S == 1) {
-            inv_stage<P, 0, true, TwConst>(tau, ld_g, st_g);
+            inv_stage<P, 0, true, TwS>(tau, ld_g, st_g);
         } else if constexpr (PH == 0) {
-            inv_stage<P, P::S - 1, false, TwConst>(tau, ld_g, st_s);
+            inv_stage<P, P::S - 1, false, TwS>(tau, ld_g, st_s);
         } else if constexpr (PH < P::S - 1) {
-            inv_stage<P, P::S - 1 - PH, false, TwConst>(tau, ld_s, st_s);
+            inv_stage<P, P::S - 1 - PH, false, TwS>(tau, ld_s, st_s);
         } else {
-            inv_stage<P, 0, true, TwConst>(tau, ld_s, st_g);
+            inv_stage<P, 0, true, TwS>(tau, ld_s, st_g);
         }
     }
 };
@@ -439,9 +494,16 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
     static_assert(L % RBt == 0, "row batches must tile the plane");
     static constexpr int nWB = L / RBt;
     static constexpr int RS = N + 1;
+#ifdef LCT_PLANE_TW_CONST
+    using TwP = TwConst;
+    static constexpr size_t kTwBytes = 0;
+#else
+    using TwP = TwShared<L>;
+    static constexpr size_t kTwBytes = TwP::kBytes;
+#endif
     // plane T[L][RS] + side buffer X[RBt][RS]: the odd-parity transform of a row batch is exchanged
     // through X while the even one uses the rows' own slots, so both run in the same three phases
-    static constexpr size_t kSmem = (size_t)(L + RBt) * RS * sizeof(float2);
+    static constexpr size_t kSmem = kTwBytes + (size_t)(L + RBt) * RS * sizeof(float2);
     static constexpr int kPhases = 2 + nWB * 3 + 2;
     static constexpr int EW = PWp::E;
     static constexpr bool kWarpSync = false;
@@ -453,8 +515,15 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
     static void grid(const Params& p, int& gx, int& gy) { gx = p.C; gy = p.M + 1; }   // c fastest: filter plane reused from L2
     static int iterations(const Params&) { return 1; }
 
+    static constexpr bool kHasPrologue = true;
+    static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) {
+#ifndef LCT_PLANE_TW_CONST
+        TwP::fill(smem, tid, kThreads);
+#endif
+    }
+
     template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem, int tid, int bx, int by, int) {
-        float2* T = reinterpret_cast<float2*>(smem);
+        float2* T = reinterpret_cast<float2*>(smem + kTwBytes);
         float2* X = T + L * RS;
         const int kt = by;
         const size_t plane = (size_t)bx * (p.M + 1) + kt;
@@ -467,11 +536,11 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
                 const int col = hb * CB + tid % CB;
                 const float2* src = p.s1 + plane * N * N + col;
                 if constexpr (PH == 0) {
-                    fwd_stage<PHp, 0, true, TwConst>(tau,
+                    fwd_stage<PHp, 0, true, TwP>(tau,
                         [&](int pos, int) { return src[(size_t)pos * N]; },
                         [&](int pos, int, float2 v) { T[pos * RS + col] = v; });
                 } else {
-                    fwd_stage<PHp, 1, false, TwConst>(tau,
+                    fwd_stage<PHp, 1, false, TwP>(tau,
                         [&](int pos, int) { return T[pos * RS + col]; },
                         [&](int pos, int, float2 v) { T[pos * RS + col] = v; });
                 }
@@ -486,11 +555,11 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
             if constexpr (st3 == 0) {
                 float2 in[EW];
                 for_each_slot<PWp, 0>(tau, [&](int pos, int slot) { in[slot] = Tr[pos]; });
-                fwd_stage<PWp, 0, false, TwConst>(tau,
+                fwd_stage<PWp, 0, false, TwP>(tau,
                     [&](int, int slot) { return in[slot]; },
                     [&](int pos, int, float2 v) { Tr[pos] = v; });
-                fwd_stage<PWp, 0, false, TwConst>(tau,
-                    [&](int pos, int slot) { return cmul(in[slot], TwConst::get(pos * (kTwN / L))); },
+                fwd_stage<PWp, 0, false, TwP>(tau,
+                    [&](int pos, int slot) { return cmul(in[slot], TwP::get(pos * (kTwN / L))); },
                     [&](int pos, int, float2 v) { Xr[pos] = v; });
 #if !defined(LCT_EMULATE) && defined(LCT_PLANE_PREFETCH)
                 {   // pull next phase's filter values from L2 towards L1 while the exchange settles
@@ -511,27 +580,27 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
                     wb_[slot] = LCT_LDG(q + L);
                 });
                 float2 b[EW];
-                fwd_stage<PWp, 1, false, TwConst>(tau,
+                fwd_stage<PWp, 1, false, TwP>(tau,
                     [&](int pos, int) { return Tr[pos]; },
                     [&](int, int slot, float2 v) { b[slot] = p.conj_filter ? cmulc(v, wa[slot]) : cmul(v, wa[slot]); });
-                inv_stage<PWp, 1, false, TwConst>(tau,
+                inv_stage<PWp, 1, false, TwP>(tau,
                     [&](int, int slot) { return b[slot]; },
                     [&](int pos, int, float2 v) { Tr[pos] = v; });
-                fwd_stage<PWp, 1, false, TwConst>(tau,
+                fwd_stage<PWp, 1, false, TwP>(tau,
                     [&](int pos, int) { return Xr[pos]; },
                     [&](int, int slot, float2 v) { b[slot] = p.conj_filter ? cmulc(v, wb_[slot]) : cmul(v, wb_[slot]); });
-                inv_stage<PWp, 1, false, TwConst>(tau,
+                inv_stage<PWp, 1, false, TwP>(tau,
                     [&](int, int slot) { return b[slot]; },
                     [&](int pos, int, float2 v) { Xr[pos] = v; });
             } else {
                 float2 ya[EW];
-                inv_stage<PWp, 0, false, TwConst>(tau,
+                inv_stage<PWp, 0, false, TwP>(tau,
                     [&](int pos, int) { return Tr[pos]; },
                     [&](int, int slot, float2 v) { ya[slot] = v; });
-                inv_stage<PWp, 0, false, TwConst>(tau,
+                inv_stage<PWp, 0, false, TwP>(tau,
                     [&](int pos, int) { return Xr[pos]; },
                     [&](int pos, int slot, float2 v) {
-                        Tr[pos] = cadd(ya[slot], cmulc(v, TwConst::get(pos * (kTwN / L))));
+                        Tr[pos] = cadd(ya[slot], cmulc(v, TwP::get(pos * (kTwN / L))));
                     });
             }
         } else {
@@ -542,11 +611,11 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
                 const int col = hb * CB + tid % CB;
                 float2* dst = p.s1 + plane * N * N + col;
                 if constexpr (s == 0) {
-                    inv_stage<PHp, 1, false, TwConst>(tau,
+                    inv_stage<PHp, 1, false, TwP>(tau,
                         [&](int pos, int) { return T[pos * RS + col]; },
                         [&](int pos, int, float2 v) { T[pos * RS + col] = v; });
                 } else {
-                    inv_stage<PHp, 0, true, TwConst>(tau,
+                    inv_stage<PHp, 0, true, TwP>(tau,
                         [&](int pos, int) { return T[pos * RS + col]; },
                         [&](int pos, int, float2 v) { dst[(size_t)pos * N] = v; });
                 }
@@ -558,6 +627,9 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
 // ---------------------------------------------------------------------------
 // generic kernel driver
 // ---------------------------------------------------------------------------
+template <class K, class = void> struct has_prologue { static constexpr bool value = false; };
+template <class K> struct has_prologue<K, decltype((void)K::kHasPrologue)> { static constexpr bool value = true; };
+
 #ifndef LCT_EMULATE
 template <class K, int PH> struct PhaseLoop {
     static LCT_DEV void run(const Params& p, typename K::Regs& r, unsigned char* smem, int it) {
@@ -570,6 +642,10 @@ template <class K, int PH> struct PhaseLoop {
 template <class K> __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) lct_kernel(const Params p, const int iters) {
     extern __shared__ __align__(16) unsigned char smem[];
     typename K::Regs r;
+    if constexpr (has_prologue<K>::value) {
+        K::prologue(p, r, smem, threadIdx.x, blockIdx.x, blockIdx.y);
+        __syncthreads();
+    }
     for (int it = 0; it < iters; ++it) PhaseLoop<K, 0>::run(p, r, smem, it);
 }
 #endif

@@ -44,6 +44,12 @@ struct EmuLauncher {
                 // poison shared memory so reads of never-written slots surface as NaN
                 float* f = reinterpret_cast<float*>(smem.data());
                 for (size_t i = 0; i < smem.size() / 4; ++i) f[i] = std::numeric_limits<float>::quiet_NaN();
+                if constexpr (lct::has_prologue<K>::value) {
+                    if (!g_reverse_threads)
+                        for (int tid = 0; tid < K::kThreads; ++tid) K::prologue(p, regs[tid], smem.data(), tid, bx, by);
+                    else
+                        for (int tid = K::kThreads - 1; tid >= 0; --tid) K::prologue(p, regs[tid], smem.data(), tid, bx, by);
+                }
                 for (int it = 0; it < iters; ++it) EmuPhases<K, 0>::run(p, regs, smem.data(), bx, by, it);
             }
         return 0;
