@@ -218,7 +218,8 @@ int lct_plan_create(const lct_desc* d, lct_plan** out) {
     LCT_TRY(upload_band(ht.mtxi_ell_falloff, ht.mtxi_rowptr, ht.mtxi_vals_falloff, p->mtxi_falloff));
     float2* dev_filt = nullptr;
     if (lct::plane_fusable(N) && !(d->reserved & LCT_FLAG_NO_PLANE_FUSION)) {
-        // fused layout: [kt][kw][plane row], rows in the order the forward H stages leave them
+        // fused layout: [kt][kw/2][plane row][kw&1] -- both output parities of a row in one 128-bit load,
+        // rows in the order the forward H stages leave them
         const int L = 2 * N;
         const float2* nat = reinterpret_cast<const float2*>(d->filter_half);
         std::vector<float2> perm(nfilt);
@@ -231,7 +232,7 @@ int lct_plan_create(const lct_desc* d, lct_plan** out) {
         for (int kt = 0; kt <= M; ++kt)
             for (int kw = 0; kw < L; ++kw)
                 for (int r = 0; r < L; ++r)
-                    perm[((size_t)kt * L + kw) * L + r] = nat[((size_t)kt * L + kh_of_row[r]) * L + kw];
+                    perm[(((size_t)kt * N + (kw >> 1)) * L + r) * 2 + (kw & 1)] = nat[((size_t)kt * L + kh_of_row[r]) * L + kw];
         LCT_TRY(to_device(perm.data(), nfilt, &p->filt_plane));
         dev_filt = p->filt_plane;
     } else {

@@ -28,14 +28,26 @@ namespace lct {
 
 #ifdef LCT_EMULATE
 extern float2 h_tw[kTwN];
-struct TwConst { static inline float2 get(int i) { return h_tw[i]; } };
-struct TwGlobal { static inline float2 get(int i) { return h_tw[i]; } };
+struct TwConst {
+    static inline float2 get(int i) { return h_tw[i]; }
+    static inline float2 mul(float2 a, int i) { return cmul(a, get(i)); }
+    static inline float2 mulc(float2 a, int i) { return cmulc(a, get(i)); }
+};
+struct TwGlobal : TwConst {};
 #define LCT_LDG(p) (*(p))
 #else
 __constant__ float2 c_tw[kTwN];          // exp(-2*pi*i*j/1024), built in double on the host
 __device__ float2 g_tw[kTwN];            // same table in global memory for lane-divergent lookups
-struct TwConst { static LCT_DEV float2 get(int i) { return c_tw[i]; } };
-struct TwGlobal { static LCT_DEV float2 get(int i) { return __ldg(&g_tw[i]); } };
+struct TwConst {
+    static LCT_DEV float2 get(int i) { return c_tw[i]; }
+    static LCT_DEV float2 mul(float2 a, int i) { return cmul(a, get(i)); }      // a * w^i
+    static LCT_DEV float2 mulc(float2 a, int i) { return cmulc(a, get(i)); }    // a * conj(w^i)
+};
+struct TwGlobal {
+    static LCT_DEV float2 get(int i) { return __ldg(&g_tw[i]); }
+    static LCT_DEV float2 mul(float2 a, int i) { return cmul(a, get(i)); }
+    static LCT_DEV float2 mulc(float2 a, int i) { return cmulc(a, get(i)); }
+};
 #define LCT_LDG(p) __ldg(p)
 #endif
 
@@ -43,6 +55,8 @@ struct TwGlobal { static LCT_DEV float2 get(int i) { return __ldg(&g_tw[i]); } }
 struct TwNone {
     static constexpr size_t kBytes = 0;
     static LCT_DEV float2 get(int i) { return TwConst::get(i); }
+    static LCT_DEV float2 mul(float2 a, int i) { return TwConst::mul(a, i); }
+    static LCT_DEV float2 mulc(float2 a, int i) { return TwConst::mulc(a, i); }
     static LCT_DEV void fill(unsigned char*, int, int) {}
 };
 
@@ -50,6 +64,8 @@ struct TwNone {
 // (entries w_L^j, j < L): a warp-uniform LDS broadcast has a shorter, steadier latency than an
 // indexed constant-bank load, and these loads sit on the critical path of every butterfly.
 template <int L> struct TwShared {
+    // (a table that also held the conjugates, for two-instruction packed multiplies, was measured
+    //  slower: its 128-bit broadcast loads cost twice the shared-memory pipe time of these 64-bit ones)
     static constexpr int kEntries = L;
     static constexpr size_t kBytes = (size_t)L * sizeof(float2);
 #ifdef LCT_EMULATE
@@ -64,15 +80,17 @@ template <int L> struct TwShared {
         for (int j = tid; j < L; j += nthreads) reinterpret_cast<float2*>(smem)[j] = c_tw[j * (kTwN / L)];
     }
 #endif
+    static LCT_DEV float2 mul(float2 a, int i) { return cmul(a, get(i)); }
+    static LCT_DEV float2 mulc(float2 a, int i) { return cmulc(a, get(i)); }
 };
 
 // Line-thread index shared by a whole warp (column tiles are multiples of 32 wide): broadcasting it
-// from lane 0 tells the compiler it is warp-uniform, so twiddle-table lookups indexed by it become
-// uniform constant loads held in uniform registers instead of per-thread LDC + vector registers.
+// through a warp reduction lands it in a uniform register, so table lookups indexed by it can be
+// uniform loads.
 #ifdef LCT_EMULATE
 static inline int warp_uniform(int v) { return v; }
 #else
-LCT_DEV int warp_uniform(int v) { return __reduce_max_sync(0xffffffffu, v); }   // REDUX writes a uniform register
+LCT_DEV int warp_uniform(int v) { return __reduce_max_sync(0xffffffffu, v); }
 #endif
 template <int LANES> LCT_DEV int line_thread(int tid) {
     if constexpr (LANES % 32 == 0) return warp_uniform(tid / LANES);
@@ -310,10 +328,10 @@ template <class P, int CT_> struct TimeInv {
             float* d = dst + (size_t)tau * NN;
             const size_t step = (size_t)P::TL * NN;
             const float* vc = vol + col;
+            const float4* ell = reinterpret_cast<const float4*>(smem + kWork);
 #ifndef LCT_EMULATE
 #pragma unroll 4
 #endif
-            const float4* ell = reinterpret_cast<const float4*>(smem + kWork);
             for (int j = tau; j < p.out_T; j += P::TL, d += step) *d = band_dot(p, ell, be + j, vc, CT);
         }
     }
@@ -479,8 +497,7 @@ template <class P, int RB_> struct ColFilter {
 //                output frequencies, the odd one pre-rotated by w_2N^n); each is filtered and
 //                inverted -- the even one in the row's own N slots, the odd one in a 1-batch side
 //                buffer -- and the two results recombined (y = y_even + conj(w_2N^n) y_odd).  Lanes run along H here, so twiddles are
-//                warp-uniform constant-bank reads and the filter, stored as [kt][kw][row], is
-//                read coalesced.
+//                warp-uniform and the filter, stored as [kt][kw/2][row][kw&1], is read coalesced.
 //   H inverse  : K4's stages, written back over the input plane in S1.
 // ---------------------------------------------------------------------------
 template <class PHp, class PWp, int NT_> struct PlaneFilter {
@@ -509,6 +526,9 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
     static constexpr bool kWarpSync = false;
 #ifndef LCT_PLANE_MINBLOCKS
 #define LCT_PLANE_MINBLOCKS 2
+#endif
+#ifndef LCT_NO_PLANE_PREFETCH
+#define LCT_PLANE_PREFETCH 1
 #endif
     static constexpr int kMinBlocks = (LCT_PLANE_MINBLOCKS * kSmem <= 220 * 1024) ? LCT_PLANE_MINBLOCKS : 1;
     struct Regs {};
@@ -559,25 +579,24 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
                     [&](int, int slot) { return in[slot]; },
                     [&](int pos, int, float2 v) { Tr[pos] = v; });
                 fwd_stage<PWp, 0, false, TwP>(tau,
-                    [&](int pos, int slot) { return cmul(in[slot], TwP::get(pos * (kTwN / L))); },
+                    [&](int pos, int slot) { return TwP::mul(in[slot], pos * (kTwN / L)); },
                     [&](int pos, int, float2 v) { Xr[pos] = v; });
 #if !defined(LCT_EMULATE) && defined(LCT_PLANE_PREFETCH)
                 {   // pull next phase's filter values from L2 towards L1 while the exchange settles
-                    const float2* f = p.filt + (size_t)kt * L * L + row;
+                    const float4* f = reinterpret_cast<const float4*>(p.filt) + (size_t)kt * N * L + row;
                     for_each_slot<PWp, 1>(tau, [&](int pos, int) {
-                        const float2* q = f + (size_t)(2 * PWp::pos_to_freq(pos)) * L;
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(q + L));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(f + (size_t)PWp::pos_to_freq(pos) * L));
                     });
                 }
 #endif
             } else if constexpr (st3 == 1) {
-                const float2* f = p.filt + (size_t)kt * L * L + row;          // [kt][kw][row]
+                // filter stored [kt][kw/2][row][kw&1]: one 128-bit load brings both parities' values
+                const float4* f = reinterpret_cast<const float4*>(p.filt) + (size_t)kt * N * L + row;
                 float2 wa[EW], wb_[EW];
                 for_each_slot<PWp, 1>(tau, [&](int pos, int slot) {
-                    const float2* q = f + (size_t)(2 * PWp::template freq_of<1>(pos, slot)) * L;
-                    wa[slot] = LCT_LDG(q);
-                    wb_[slot] = LCT_LDG(q + L);
+                    const float4 w = LCT_LDG(f + (size_t)PWp::template freq_of<1>(pos, slot) * L);
+                    wa[slot] = make_float2(w.x, w.y);
+                    wb_[slot] = make_float2(w.z, w.w);
                 });
                 float2 b[EW];
                 fwd_stage<PWp, 1, false, TwP>(tau,
@@ -600,7 +619,7 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
                 inv_stage<PWp, 0, false, TwP>(tau,
                     [&](int pos, int) { return Xr[pos]; },
                     [&](int pos, int slot, float2 v) {
-                        Tr[pos] = cadd(ya[slot], cmulc(v, TwP::get(pos * (kTwN / L))));
+                        Tr[pos] = cadd(ya[slot], TwP::mulc(v, pos * (kTwN / L)));
                     });
             }
         } else {

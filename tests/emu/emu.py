@@ -46,10 +46,11 @@ class EmuPlan:
         self.falloff = np.ascontiguousarray(ops.falloff(M, material), np.float32)
         w = ops.inverse_filter_half(N, M, ops.slope_for(M, bin_len, wall_size), method)
         self.filt = np.ascontiguousarray((w * np.float32(1.0 / (8.0 * M * N * N))).astype(np.complex64))
-        # fused layout [kt][kw][plane row], rows in the H plan's position order (what lct_plan_create builds)
+        # fused layout [kt][kw/2][plane row][kw&1], rows in the H plan's position order (what lct_plan_create builds)
         L = 2 * N
         kh = np.array([lib().lct_emu_plane_row_freq(N, r) for r in range(L)])
-        self.filt_plane = np.ascontiguousarray(self.filt[:, kh, :].transpose(0, 2, 1)) if N <= 64 else None
+        self.filt_plane = (np.ascontiguousarray(self.filt[:, kh, :].reshape(M + 1, L, N, 2).transpose(0, 2, 1, 3))
+                           if N <= 64 else None)
 
     def run(self, inp, D, Tin, be, backward=False, mask=31, reverse=False, s1=None, s2=None, fused=True):
         M, N = self.M, self.N
