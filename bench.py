@@ -49,6 +49,15 @@ def stage_bytes(M, N, C):
     return [12 * V * C, 24 * V * C, 32 * V * C + 32 * V, 24 * V * C, 12 * V * C]
 
 
+def ncu_traffic(workload, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (or None)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload, {}).get(kernel)
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -121,7 +130,7 @@ def cpu_oracle_rate(M, N, reps, warm, threads=None):
     return times
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, out):
     """`--impl reference`: the reference's own CPU implementation of the path (the oracle port:
     /root/reference cannot travel to the GPU box) on the host cores; rank 0 only."""
     if rank != 0:
@@ -141,10 +150,20 @@ def run_reference(args, rank):
                                    f"{torch.get_num_threads()} threads"},
         "e2e": {"value": value, "unit": "transients/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
+
+
+def claim_stdout():
+    """Route everything libraries print on fd 1 (NCCL's version banner, ...) to stderr and return a
+    handle on the real stdout: the contract is ONE JSON line there."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
+    real_stdout = claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -161,7 +180,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, real_stdout)
         return
 
     import torch.distributed as dist
@@ -308,7 +327,8 @@ def main():
             "fwd_bwd": {"value": world * B * K / (fb_ms * 1e-3), "unit": "transients/s", "ms_per_step": fb_ms / K,
                         "gpu_launches": 2 * n_kernels * K},
             "roofline": {"bound": "hbm", "kernel": stages[top]["kernel"], "achieved": stages[top]["gbs"], "peak": peak,
-                         "unit": "GB/s", "frac": stages[top]["frac"], "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": stages[top]["frac"],
+                         "traffic": ncu_traffic(args.workload, stages[top]["kernel"]), "peak_source": peak_src,
                          "chain": {"bytes": chain_bytes, "gbs": chain_gbs, "frac": chain_gbs / peak,
                                    "note": "A = 104*V*C + 32*V (SURVEY 8d contract figure) over the headline step time"},
                          "serial_ms_per_step": serial_ms,
@@ -316,14 +336,14 @@ def main():
                                  "channel groups on two streams so consecutive kernels overlap"},
             "stages": stages,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only
             times = cpu_oracle_rate(M, N, args.cpu_reps, 2)
             line["cpu_baseline"] = {
                 "value": 1.0 / statistics.median(times), "unit": "transients/s", "cores": torch.get_num_threads(),
                 "kind": "port",
                 "sample": f"{args.cpu_reps} forwards of one 1x1x{M}x{N}x{N} transient (oracle port of tflct.py:94-179, "
                           f"torch CPU fp32), median; host has {os.cpu_count()} logical cores"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
