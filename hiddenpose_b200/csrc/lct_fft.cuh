@@ -248,7 +248,7 @@ LCT_DEV void fwd_stage(int tau, LD ld, ST stf) {
         }
         if constexpr (s < P::S - 1) {
             LCT_UNROLL
-            for (int k = 1; k < r; ++k) a[k] = TW::mul(a[k], (k * lo) * (kTwN / Ls));
+            for (int k = 1; k < r; ++k) a[k] = TW::template stage_mul<Ls, str>(a[k], k, lo);
         }
         LCT_UNROLL
         for (int k = 0; k < r; ++k) stf(base + k * str, m * r + k, a[k]);
@@ -270,7 +270,7 @@ LCT_DEV void inv_stage(int tau, LD ld, ST stf) {
         for (int k = 0; k < r; ++k) a[k] = ld(base + k * str, m * r + k);
         if constexpr (s < P::S - 1) {
             LCT_UNROLL
-            for (int k = 1; k < r; ++k) a[k] = TW::mulc(a[k], (k * lo) * (kTwN / Ls));
+            for (int k = 1; k < r; ++k) a[k] = TW::template stage_mulc<Ls, str>(a[k], k, lo);
         }
         if constexpr (LOWER_ONLY) {
             dft_lower_only<r, true>(a);

@@ -22,6 +22,8 @@
 // (SURVEY.md section 3.5).
 #pragma once
 
+#include <type_traits>
+
 #include "lct_fft.cuh"
 
 namespace lct {
@@ -32,8 +34,13 @@ struct TwConst {
     static inline float2 get(int i) { return h_tw[i]; }
     static inline float2 mul(float2 a, int i) { return cmul(a, get(i)); }
     static inline float2 mulc(float2 a, int i) { return cmulc(a, get(i)); }
+    template <int Ls, int STR> static LCT_DEV float2 stage_mul(float2 a, int k, int lo) { return mul(a, (k * lo) * (kTwN / Ls)); }
+    template <int Ls, int STR> static LCT_DEV float2 stage_mulc(float2 a, int k, int lo) { return mulc(a, (k * lo) * (kTwN / Ls)); }
 };
-struct TwGlobal : TwConst {};
+struct TwGlobal : TwConst {
+    static constexpr size_t kBytes = 0;
+    static inline void fill(unsigned char*, int, int) {}
+};
 #define LCT_LDG(p) (*(p))
 #else
 __constant__ float2 c_tw[kTwN];          // exp(-2*pi*i*j/1024), built in double on the host
@@ -42,11 +49,17 @@ struct TwConst {
     static LCT_DEV float2 get(int i) { return c_tw[i]; }
     static LCT_DEV float2 mul(float2 a, int i) { return cmul(a, get(i)); }      // a * w^i
     static LCT_DEV float2 mulc(float2 a, int i) { return cmulc(a, get(i)); }    // a * conj(w^i)
+    template <int Ls, int STR> static LCT_DEV float2 stage_mul(float2 a, int k, int lo) { return mul(a, (k * lo) * (kTwN / Ls)); }
+    template <int Ls, int STR> static LCT_DEV float2 stage_mulc(float2 a, int k, int lo) { return mulc(a, (k * lo) * (kTwN / Ls)); }
 };
 struct TwGlobal {
+    static constexpr size_t kBytes = 0;
+    static LCT_DEV void fill(unsigned char*, int, int) {}
     static LCT_DEV float2 get(int i) { return __ldg(&g_tw[i]); }
     static LCT_DEV float2 mul(float2 a, int i) { return cmul(a, get(i)); }
     static LCT_DEV float2 mulc(float2 a, int i) { return cmulc(a, get(i)); }
+    template <int Ls, int STR> static LCT_DEV float2 stage_mul(float2 a, int k, int lo) { return mul(a, (k * lo) * (kTwN / Ls)); }
+    template <int Ls, int STR> static LCT_DEV float2 stage_mulc(float2 a, int k, int lo) { return mulc(a, (k * lo) * (kTwN / Ls)); }
 };
 #define LCT_LDG(p) __ldg(p)
 #endif
@@ -57,6 +70,8 @@ struct TwNone {
     static LCT_DEV float2 get(int i) { return TwConst::get(i); }
     static LCT_DEV float2 mul(float2 a, int i) { return TwConst::mul(a, i); }
     static LCT_DEV float2 mulc(float2 a, int i) { return TwConst::mulc(a, i); }
+    template <int Ls, int STR> static LCT_DEV float2 stage_mul(float2 a, int k, int lo) { return mul(a, (k * lo) * (kTwN / Ls)); }
+    template <int Ls, int STR> static LCT_DEV float2 stage_mulc(float2 a, int k, int lo) { return mulc(a, (k * lo) * (kTwN / Ls)); }
     static LCT_DEV void fill(unsigned char*, int, int) {}
 };
 
@@ -82,6 +97,38 @@ template <int L> struct TwShared {
 #endif
     static LCT_DEV float2 mul(float2 a, int i) { return cmul(a, get(i)); }
     static LCT_DEV float2 mulc(float2 a, int i) { return cmulc(a, get(i)); }
+    template <int Ls, int STR> static LCT_DEV float2 stage_mul(float2 a, int k, int lo) { return mul(a, (k * lo) * (kTwN / Ls)); }
+    template <int Ls, int STR> static LCT_DEV float2 stage_mulc(float2 a, int k, int lo) { return mulc(a, (k * lo) * (kTwN / Ls)); }
+};
+
+// Stage-0 twiddles of a line plan, laid out [k][lo] at the start of shared memory: the lanes of a
+// line (consecutive lo) read consecutive entries, so the lane-divergent lookup is conflict-free.
+template <class P> struct TwLine {
+    static constexpr int L = P::L, STR0 = P::st(0);
+    static constexpr size_t kBytes = (size_t)L * sizeof(float2);
+#ifdef LCT_EMULATE
+    static inline float2 at(int k, int lo) { return h_tw[(k * lo) * (kTwN / L)]; }
+    static inline void fill(unsigned char*, int, int) {}
+#else
+    static LCT_DEV float2 at(int k, int lo) {
+        extern __shared__ __align__(16) unsigned char lct_dyn_smem[];
+        return reinterpret_cast<const float2*>(lct_dyn_smem)[k * STR0 + lo];
+    }
+    static LCT_DEV void fill(unsigned char* smem, int tid, int nthreads) {
+        for (int j = tid; j < L; j += nthreads) {
+            const int k = j / STR0, lo = j % STR0;
+            reinterpret_cast<float2*>(smem)[j] = c_tw[((k * lo) % L) * (kTwN / L)];
+        }
+    }
+#endif
+    template <int Ls, int STR> static LCT_DEV float2 stage_mul(float2 a, int k, int lo) {
+        static_assert(Ls == L && STR == STR0, "TwLine only serves the first stage");
+        return cmul(a, at(k, lo));
+    }
+    template <int Ls, int STR> static LCT_DEV float2 stage_mulc(float2 a, int k, int lo) {
+        static_assert(Ls == L && STR == STR0, "TwLine only serves the first stage");
+        return cmulc(a, at(k, lo));
+    }
 };
 
 // Line-thread index shared by a whole warp (column tiles are multiples of 32 wide): broadcasting it
@@ -426,13 +473,15 @@ template <class P, int RB_> struct ColFilter {
     static_assert(32 % P::TL == 0, "the threads of one line must share a warp");
     static constexpr int L = P::L, N = L / 2, RB = RB_, kThreads = P::TL * RB;
     static constexpr int kPhases = 3;
+    // block-local [k][lo] table for the 8/16-wide plans; the 32-wide plan (N = 256) measured faster on __ldg
+    using TwL = typename std::conditional<(P::E <= 16), TwLine<P>, TwGlobal>::type;
     // all threads of a line sit in one warp (tid % TL), so the exchanges only need __syncwarp:
     // warps run through the channel loop independently of each other.
     static constexpr bool kWarpSync = true;
     static constexpr int kMinBlocks = (P::E <= 16) ? 2 : 1;
     static constexpr int PAD = 1;
     static constexpr int RS = L + P::R0 * PAD + ((P::TL < 16) ? 8 : 0);    // row stride in float2
-    static constexpr size_t kSmem = (size_t)RB * RS * sizeof(float2);
+    static constexpr size_t kSmem = TwL::kBytes + (size_t)RB * RS * sizeof(float2);
     static constexpr int kIn = P::E / 2;                                   // non-zero inputs per thread
     struct Regs { float2 w[P::E]; float2 pre[kIn]; };
     static void grid(const Params& p, int& gx, int& gy) { gx = L / RB; gy = p.M + 1; }
@@ -450,10 +499,13 @@ template <class P, int RB_> struct ColFilter {
         }
     }
 
+    static constexpr bool kHasPrologue = true;
+    static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwL::fill(smem, tid, kThreads); }
+
     template <int PH> static LCT_DEV void phase(const Params& p, Regs& r, unsigned char* smem, int tid, int bx, int by, int it) {
         const int tau = tid % P::TL, rl = tid / P::TL;
         const int kh = bx * RB + rl, kt = by, c = it;
-        float2* zs = reinterpret_cast<float2*>(smem) + rl * RS;
+        float2* zs = reinterpret_cast<float2*>(smem + TwL::kBytes) + rl * RS;
         const size_t chan = (size_t)(p.M + 1) * L * N;
         float2* row = p.s2 + (size_t)c * chan + ((size_t)kt * L + kh) * N;
         if constexpr (PH == 0) {
@@ -467,20 +519,20 @@ template <class P, int RB_> struct ColFilter {
                 });
             }
             constexpr int r0 = P::R0;
-            fwd_stage<P, 0, true, TwGlobal>(tau,
+            fwd_stage<P, 0, true, TwL>(tau,
                 [&](int, int slot) { return r.pre[(slot / r0) * (r0 / 2) + (slot % r0)]; },
                 [&](int pos, int, float2 v) { zs[padpos(pos)] = v; });
             if (it + 1 < p.C) fetch(row + chan, tau, r);        // next channel's row flies during this one's math
         } else if constexpr (PH == 1) {
             float2 a[P::E];
-            fwd_stage<P, 1, false, TwGlobal>(tau,
+            fwd_stage<P, 1, false, TwL>(tau,
                 [&](int pos, int) { return zs[padpos(pos)]; },
                 [&](int, int slot, float2 v) { a[slot] = cmul(v, r.w[slot]); });
-            inv_stage<P, 1, false, TwGlobal>(tau,
+            inv_stage<P, 1, false, TwL>(tau,
                 [&](int, int slot) { return a[slot]; },
                 [&](int pos, int, float2 v) { zs[padpos(pos)] = v; });
         } else {
-            inv_stage<P, 0, true, TwGlobal>(tau,
+            inv_stage<P, 0, true, TwL>(tau,
                 [&](int pos, int) { return zs[padpos(pos)]; },
                 [&](int pos, int, float2 v) { row[pos] = v; });
         }
