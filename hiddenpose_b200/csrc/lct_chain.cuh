@@ -15,7 +15,15 @@ template <> struct ColPlan<32>  { using type = Plan<8, 4>; };
 template <> struct ColPlan<64>  { using type = Plan<8, 8>; };
 template <> struct ColPlan<128> { using type = Plan<16, 8>; };
 template <> struct ColPlan<256> { using type = Plan<16, 16>; };
-template <> struct ColPlan<512> { using type = Plan<8, 8, 8>; };
+template <> struct ColPlan<512> { using type = Plan<16, 32>; };    // measured on cfg3: (8,8,8) 590 us, (16,32) 355-447 us
+
+// The two time kernels may prefer different factorizations of the same length.
+template <int M> struct TimeFwdPlan { using type = typename ColPlan<M>::type; };
+template <int M> struct TimeInvPlan { using type = typename ColPlan<M>::type; };
+template <> struct TimeFwdPlan<512> { using type = Plan<16, 16, 2>; };   // 410 us vs 447 us with (16,32)
+template <int L> struct RowFwdPlan { using type = typename ColPlan<L>::type; };
+template <int L> struct RowInvPlan { using type = typename ColPlan<L>::type; };
+template <> struct RowFwdPlan<512> { using type = Plan<8, 8, 8>; };        // cfg5: 373 us vs 412 us with (16,32)
 
 // Line plans for K3 (lanes run along the contiguous line): two stages only.
 template <int L> struct LinePlan;
@@ -59,16 +67,16 @@ constexpr bool supported_N(int N) { return N == 8 || N == 16 || N == 32 || N == 
 enum ChainStage { kStageTimeFwd = 1, kStageRowFwd = 2, kStageColFilter = 4, kStageRowInv = 8, kStageTimeInv = 16, kStageAll = 31 };
 
 template <int M, class Launcher> int launch_time_fwd(const Params& p, Launcher& l) {
-    return l.template launch<TimeFwd<typename ColPlan<M>::type, TimeTile<M>::CT>>(p);
+    return l.template launch<TimeFwd<typename TimeFwdPlan<M>::type, TimeTile<M>::CT>>(p);
 }
 template <int M, class Launcher> int launch_time_inv(const Params& p, Launcher& l) {
-    return l.template launch<TimeInv<typename ColPlan<M>::type, TimeTile<M>::CT>>(p);
+    return l.template launch<TimeInv<typename TimeInvPlan<M>::type, TimeTile<M>::CT>>(p);
 }
 template <int N, class Launcher> int launch_row_fwd(const Params& p, Launcher& l) {
-    return l.template launch<RowFwd<typename ColPlan<2 * N>::type, RowTile<N>::CT>>(p);
+    return l.template launch<RowFwd<typename RowFwdPlan<2 * N>::type, RowTile<N>::CT>>(p);
 }
 template <int N, class Launcher> int launch_row_inv(const Params& p, Launcher& l) {
-    return l.template launch<RowInv<typename ColPlan<2 * N>::type, RowTile<N>::CT>>(p);
+    return l.template launch<RowInv<typename RowInvPlan<2 * N>::type, RowTile<N>::CT>>(p);
 }
 template <int N, class Launcher> int launch_col_filter(const Params& p, Launcher& l) {
     return l.template launch<ColFilter<typename LinePlan<2 * N>::type, LineRows<N>::RB>>(p);

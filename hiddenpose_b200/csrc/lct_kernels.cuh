@@ -205,9 +205,9 @@ template <class P, int CT_> struct TimeFwd {
     static constexpr size_t kWork = (size_t)M * CT * sizeof(float2);
     static constexpr size_t kSmem = TwS::kBytes + (kWork + (size_t)M * sizeof(float4));       // + the operator's row records
     static_assert((size_t)(M + 2) * CT * sizeof(float) <= kWork, "x tile must fit");
-    static_assert(M <= kThreads, "one thread per row record");
     static constexpr bool kWarpSync = false;
-    static constexpr int kMinBlocks = (kThreads >= 1024) ? 1 : 1024 / kThreads;     // 1024 threads/SM at <= 64 regs
+    // 1024 threads/SM at <= 64 regs; the 32-wide butterflies need 128 regs (512 threads/SM)
+    static constexpr int kMinBlocks = (P::E >= 32) ? (512 / kThreads > 0 ? 512 / kThreads : 1) : ((kThreads >= 1024) ? 1 : 1024 / kThreads);
     struct Regs { float2 a[P::E]; };
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N * p.N / CT; gy = p.C; }
     static int iterations(const Params&) { return 1; }
@@ -227,7 +227,7 @@ template <class P, int CT_> struct TimeFwd {
             constexpr int V4 = CT / 4, kSlots = (M + 2) * V4;
             const float4* src = reinterpret_cast<const float4*>(p.in + (size_t)c * p.in_T * NN + col0);
             float4* xs4 = reinterpret_cast<float4*>(smem);
-            if (tid < M) reinterpret_cast<float4*>(smem + kWork)[tid] = LCT_LDG(p.ell + tid);
+            for (int j = tid; j < M; j += kThreads) reinterpret_cast<float4*>(smem + kWork)[j] = LCT_LDG(p.ell + j);
             float4 v[(kSlots + kThreads - 1) / kThreads];
             LCT_UNROLL
             for (int u = 0; u < (kSlots + kThreads - 1) / kThreads; ++u) {
@@ -293,9 +293,9 @@ template <class P, int CT_> struct TimeInv {
     static constexpr int kPhases = 2 + P::S + 2;          // load | stage S-1 -> regs | scatter | middle.. | stage 0 -> regs | scatter vol | gather
     static constexpr size_t kWork = (size_t)(M + 1) * CT * sizeof(float2);
     static constexpr size_t kSmem = TwS::kBytes + (kWork + (size_t)M * sizeof(float4));       // + the operator's row records
-    static_assert(M <= kThreads, "one thread per row record");
     static constexpr bool kWarpSync = false;
-    static constexpr int kMinBlocks = (kThreads >= 1024) ? 1 : 1024 / kThreads;     // 1024 threads/SM at <= 64 regs
+    // 1024 threads/SM at <= 64 regs; the 32-wide butterflies need 128 regs (512 threads/SM)
+    static constexpr int kMinBlocks = (P::E >= 32) ? (512 / kThreads > 0 ? 512 / kThreads : 1) : ((kThreads >= 1024) ? 1 : 1024 / kThreads);
     struct Regs { float2 a[P::E]; };
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N * p.N / CT; gy = p.C; }
     static int iterations(const Params&) { return 1; }
@@ -315,7 +315,7 @@ template <class P, int CT_> struct TimeInv {
             constexpr int V2 = CT / 2, kSlots = (M + 1) * V2;
             const float4* src = reinterpret_cast<const float4*>(p.s1 + (size_t)c * (M + 1) * NN + col0);
             float4* zs4 = reinterpret_cast<float4*>(smem);
-            if (tid < M) reinterpret_cast<float4*>(smem + kWork)[tid] = LCT_LDG(p.ell + tid);
+            for (int j = tid; j < M; j += kThreads) reinterpret_cast<float4*>(smem + kWork)[j] = LCT_LDG(p.ell + j);
             float4 v[(kSlots + kThreads - 1) / kThreads];
             LCT_UNROLL
             for (int u = 0; u < (kSlots + kThreads - 1) / kThreads; ++u) {
@@ -392,7 +392,8 @@ template <class P, int CT_> struct RowFwd {
     static constexpr int L = P::L, N = L / 2, CT = CT_, kThreads = P::TL * CT;
     static constexpr int kPhases = P::S;
     static constexpr bool kWarpSync = false;
-    static constexpr int kMinBlocks = (kThreads >= 1024) ? 1 : ((1024 / kThreads) > 32 ? 32 : (1024 / kThreads));   // <= 64 regs
+    static constexpr int kMinBlocks = (P::E >= 32) ? (512 / kThreads > 0 ? 512 / kThreads : 1)
+                                                   : ((kThreads >= 1024) ? 1 : ((1024 / kThreads) > 32 ? 32 : (1024 / kThreads)));   // <= 64 regs
     static constexpr size_t kSmem = TwS::kBytes + ((P::S > 1) ? (size_t)L * CT * sizeof(float2) : 0);
     struct Regs {};
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N / CT; gy = p.C * (p.M + 1); }
@@ -431,7 +432,8 @@ template <class P, int CT_> struct RowInv {
     static constexpr int L = P::L, N = L / 2, CT = CT_, kThreads = P::TL * CT;
     static constexpr int kPhases = P::S;
     static constexpr bool kWarpSync = false;
-    static constexpr int kMinBlocks = (kThreads >= 1024) ? 1 : ((1024 / kThreads) > 32 ? 32 : (1024 / kThreads));   // <= 64 regs
+    static constexpr int kMinBlocks = (P::E >= 32) ? (512 / kThreads > 0 ? 512 / kThreads : 1)
+                                                   : ((kThreads >= 1024) ? 1 : ((1024 / kThreads) > 32 ? 32 : (1024 / kThreads)));   // <= 64 regs
     static constexpr size_t kSmem = TwS::kBytes + ((P::S > 1) ? (size_t)L * CT * sizeof(float2) : 0);
     struct Regs {};
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N / CT; gy = p.C * (p.M + 1); }
