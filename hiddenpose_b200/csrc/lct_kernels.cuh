@@ -201,26 +201,29 @@ LCT_DEV int window_begin(const Params& p, int c) {
 template <class P, int CT_> struct TimeFwd {
     using TwS = TwNone;                        // constant-bank twiddles (a block-local table measured slower here)
     static constexpr int M = P::L, CT = CT_, kThreads = P::TL * CT;
-    static constexpr int kPhases = 3 + (P::S - 1) + 1;
-    static constexpr size_t kWork = (size_t)M * CT * sizeof(float2);
-    static constexpr size_t kSmem = TwS::kBytes + (kWork + (size_t)M * sizeof(float4));       // + the operator's row records
-    static_assert((size_t)(M + 2) * CT * sizeof(float) <= kWork, "x tile must fit");
+    // phases: load x tile | gather + stage 0 -> zs | stages 1.. in place | post-process
+    static constexpr int kPhases = 2 + (P::S - 1) + 1;
+    // x tile, FFT buffer and the operator's row records side by side: the register file already caps
+    // the kernel at two blocks per SM, so nothing is gained by aliasing them (and a phase is saved)
+    static constexpr size_t kXs = ((size_t)(M + 2) * CT * sizeof(float) + 15) / 16 * 16;
+    static constexpr size_t kWork = kXs + (size_t)M * CT * sizeof(float2);
+    static constexpr size_t kSmem = TwS::kBytes + (kWork + (size_t)M * sizeof(float4));
     static constexpr bool kWarpSync = false;
     // 1024 threads/SM at <= 64 regs; the 32-wide butterflies need 128 regs (512 threads/SM)
     static constexpr int kMinBlocks = (P::E >= 32) ? (512 / kThreads > 0 ? 512 / kThreads : 1) : ((kThreads >= 1024) ? 1 : 1024 / kThreads);
-    struct Regs { float2 a[P::E]; };
+    struct Regs {};
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N * p.N / CT; gy = p.C; }
     static int iterations(const Params&) { return 1; }
 
     static constexpr bool kHasPrologue = true;
     static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwS::fill(smem, tid, kThreads); }
 
-    template <int PH> static LCT_DEV void phase(const Params& p, Regs& r, unsigned char* smem_base, int tid, int bx, int by, int) {
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem_base, int tid, int bx, int by, int) {
         unsigned char* smem = smem_base + TwS::kBytes;
         const int col = tid % CT, tau = line_thread<CT>(tid);
         const int NN = p.N * p.N, col0 = bx * CT, c = by;
         float* xs = reinterpret_cast<float*>(smem);
-        float2* zs = reinterpret_cast<float2*>(smem);
+        float2* zs = reinterpret_cast<float2*>(smem + kXs);
         if constexpr (PH == 0) {
             // x tile -> xs[(M+2)][CT] f32, zero outside the window [be, en) and in the two pad rows
             const int be = window_begin(p, c), en = be + p.in_T;
@@ -246,11 +249,9 @@ template <class P, int CT_> struct TimeFwd {
                     const float4* ell = reinterpret_cast<const float4*>(smem + kWork);
                     return make_float2(band_dot(p, ell, 2 * pos, xs + col, CT), band_dot(p, ell, 2 * pos + 1, xs + col, CT));
                 },
-                [&](int, int slot, float2 v) { r.a[slot] = v; });
-        } else if constexpr (PH == 2) {
-            for_each_slot<P, 0>(tau, [&](int pos, int slot) { zs[pos * CT + col] = r.a[slot]; });
-        } else if constexpr (PH < 2 + P::S) {
-            constexpr int s = PH - 2;
+                [&](int pos, int, float2 v) { zs[pos * CT + col] = v; });
+        } else if constexpr (PH < 1 + P::S) {
+            constexpr int s = PH - 1;
             fwd_stage<P, s, false, TwS>(tau,
                 [&](int pos, int) { return zs[pos * CT + col]; },
                 [&](int pos, int, float2 v) { zs[pos * CT + col] = v; });
@@ -290,8 +291,11 @@ template <class P, int CT_> struct TimeFwd {
 template <class P, int CT_> struct TimeInv {
     using TwS = TwNone;                        // constant-bank twiddles (a block-local table measured slower here)
     static constexpr int M = P::L, CT = CT_, kThreads = P::TL * CT;
-    static constexpr int kPhases = 2 + P::S + 2;          // load | stage S-1 -> regs | scatter | middle.. | stage 0 -> regs | scatter vol | gather
-    static constexpr size_t kWork = (size_t)(M + 1) * CT * sizeof(float2);
+    static constexpr int kPhases = 2 + P::S + 1;          // load | stage S-1 -> regs | scatter | middle.. | stage 0 -> vol | gather
+    // spectrum tile / FFT buffer (aliased: the first stage goes through registers) + the real volume
+    // tile next to it (registers cap the kernel at two blocks per SM anyway; saves a phase)
+    static constexpr size_t kZs = ((size_t)(M + 1) * CT * sizeof(float2) + 15) / 16 * 16;
+    static constexpr size_t kWork = kZs + (size_t)(M + 2) * CT * sizeof(float);
     static constexpr size_t kSmem = TwS::kBytes + (kWork + (size_t)M * sizeof(float4));       // + the operator's row records
     static constexpr bool kWarpSync = false;
     // 1024 threads/SM at <= 64 regs; the 32-wide butterflies need 128 regs (512 threads/SM)
@@ -308,7 +312,7 @@ template <class P, int CT_> struct TimeInv {
         const int col = tid % CT, tau = line_thread<CT>(tid);
         const int NN = p.N * p.N, col0 = bx * CT, c = by;
         float2* zs = reinterpret_cast<float2*>(smem);
-        float* vol = reinterpret_cast<float*>(smem);
+        float* vol = reinterpret_cast<float*>(smem + kZs);
         constexpr int SL = P::S - 1;
         if constexpr (PH == 0) {
             // spectrum tile -> zs[(M+1)][CT] c64 (128-bit loads: two columns per lane)
@@ -338,20 +342,15 @@ template <class P, int CT_> struct TimeInv {
             if constexpr (SL == 0) {
                 inv_stage<P, 0, true, TwS>(tau,
                     [&](int pos, int slot) { return z_at(P::template freq_of<0>(pos, slot)); },
-                    [&](int, int slot, float2 v) { r.a[slot] = v; });
+                    [&](int pos, int, float2 v) { vol[(2 * pos) * CT + col] = v.x; vol[(2 * pos + 1) * CT + col] = v.y; });
+                if (tau == 0) { vol[M * CT + col] = 0.f; vol[(M + 1) * CT + col] = 0.f; }
             } else {
                 inv_stage<P, SL, false, TwS>(tau,
                     [&](int pos, int slot) { return z_at(P::template freq_of<SL>(pos, slot)); },
                     [&](int, int slot, float2 v) { r.a[slot] = v; });
             }
         } else if constexpr (PH == 2) {
-            if constexpr (SL == 0) {
-                for_each_slot_lower<P, 0>(tau, [&](int pos, int slot) {
-                    vol[(2 * pos) * CT + col] = r.a[slot].x;
-                    vol[(2 * pos + 1) * CT + col] = r.a[slot].y;
-                });
-                if (tau == 0) { vol[M * CT + col] = 0.f; vol[(M + 1) * CT + col] = 0.f; }
-            } else {
+            if constexpr (SL > 0) {
                 for_each_slot<P, SL>(tau, [&](int pos, int slot) { zs[pos * CT + col] = r.a[slot]; });
             }
         } else if constexpr (PH < 2 + SL) {          // middle stages SL-1 .. 1, in place
@@ -362,12 +361,7 @@ template <class P, int CT_> struct TimeInv {
         } else if constexpr (PH == 2 + SL && SL > 0) {
             inv_stage<P, 0, true, TwS>(tau,
                 [&](int pos, int) { return zs[pos * CT + col]; },
-                [&](int, int slot, float2 v) { r.a[slot] = v; });
-        } else if constexpr (PH == 3 + SL && SL > 0) {
-            for_each_slot_lower<P, 0>(tau, [&](int pos, int slot) {
-                vol[(2 * pos) * CT + col] = r.a[slot].x;
-                vol[(2 * pos + 1) * CT + col] = r.a[slot].y;
-            });
+                [&](int pos, int, float2 v) { vol[(2 * pos) * CT + col] = v.x; vol[(2 * pos + 1) * CT + col] = v.y; });
             if (tau == 0) { vol[M * CT + col] = 0.f; vol[(M + 1) * CT + col] = 0.f; }   // pad rows for band_dot
         } else if constexpr (PH == kPhases - 1) {
             const int be = window_begin(p, c);

@@ -37,7 +37,7 @@ struct EmuLauncher {
         int gx, gy;
         K::grid(p, gx, gy);
         const int iters = K::iterations(p);
-        std::vector<unsigned char> smem(K::kSmem + 64);
+        std::vector<unsigned char> smem(K::kSmem + 64);     // 64 guard bytes: a write past kSmem trips the canary
         std::vector<typename K::Regs> regs(K::kThreads);
         for (int by = 0; by < gy; ++by)
             for (int bx = 0; bx < gx; ++bx) {
@@ -50,7 +50,10 @@ struct EmuLauncher {
                     else
                         for (int tid = K::kThreads - 1; tid >= 0; --tid) K::prologue(p, regs[tid], smem.data(), tid, bx, by);
                 }
+                std::memset(smem.data() + K::kSmem, 0xA5, 64);
                 for (int it = 0; it < iters; ++it) EmuPhases<K, 0>::run(p, regs, smem.data(), bx, by, it);
+                for (int g = 0; g < 64; ++g)
+                    if (smem[K::kSmem + g] != 0xA5) return 200;      // shared-memory overrun
             }
         return 0;
     }
