@@ -26,7 +26,8 @@ NVCC_FLAGS = [
 SYMBOLS = (
     "lct_abi_version", "lct_error_string", "lct_last_error", "lct_plan_create", "lct_plan_destroy",
     "lct_plan_time_bins", "lct_plan_spatial", "lct_plan_workspace_bytes", "lct_forward", "lct_backward",
-    "lct_bp_laplacian", "lct_forward_host", "lct_run_staged",
+    "lct_bp_laplacian", "lct_forward_host", "lct_run_staged", "lct_forward_minmax", "lct_minmax",
+    "lct_normalize_feature", "lct_normalize_feature_backward",
 )
 
 
@@ -98,6 +99,14 @@ def load():
         fn.argtypes = [vp, vp, pi32, pi32, i32, i32, i32, vp, vp, sz, vp]
     lib.lct_run_staged.restype = ctypes.c_int
     lib.lct_run_staged.argtypes = [vp, vp, pi32, pi32, i32, i32, i32, vp, vp, sz, vp, i32, ctypes.POINTER(vp)]
+    lib.lct_forward_minmax.restype = ctypes.c_int
+    lib.lct_forward_minmax.argtypes = [vp, vp, pi32, pi32, i32, i32, i32, vp, vp, vp, sz, vp]
+    lib.lct_minmax.restype = ctypes.c_int
+    lib.lct_minmax.argtypes = [vp, i32, ctypes.c_int64, vp, vp]
+    lib.lct_normalize_feature.restype = ctypes.c_int
+    lib.lct_normalize_feature.argtypes = [vp, vp, vp, i32, ctypes.c_int64, ctypes.c_float, vp]
+    lib.lct_normalize_feature_backward.restype = ctypes.c_int
+    lib.lct_normalize_feature_backward.argtypes = [vp, vp, vp, vp, vp, i32, ctypes.c_int64, ctypes.c_float, vp]
     lib.lct_bp_laplacian.restype = ctypes.c_int
     lib.lct_bp_laplacian.argtypes = [vp, vp, vp, i32, ctypes.POINTER(ctypes.c_float), i32, vp]
     lib.lct_forward_host.restype = ctypes.c_int

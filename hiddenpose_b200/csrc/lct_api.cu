@@ -13,6 +13,7 @@
 
 #include "hiddenpose_lct.h"
 #include "lct_chain.cuh"
+#include "lct_normalize.cuh"
 #include "lct_stencil.cuh"
 #include "lct_tables.h"
 
@@ -274,7 +275,7 @@ size_t lct_plan_workspace_bytes(const lct_plan* plan, int32_t channels) {
 
 static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const int32_t* ten,
                int B, int D, int Tin, float* out, void* ws, size_t ws_bytes, void* stream_, bool backward,
-               void* const* events = nullptr) {
+               void* const* events = nullptr, unsigned long long* minmax_keys = nullptr) {
     if (!plan || !in || !out || !tbe || !ten || !ws) return fail(LCT_ERR_INVALID, "null argument");
     if (B <= 0 || D <= 0 || Tin <= 0 || Tin > plan->M) return fail(LCT_ERR_INVALID, "bad shape");
     if (((uintptr_t)in | (uintptr_t)out | (uintptr_t)ws) & 15) return fail(LCT_ERR_INVALID, "buffers must be 16-byte aligned");
@@ -307,6 +308,7 @@ static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const 
     const size_t in_stride = (size_t)(backward ? M : Tin) * N * N;
     const size_t out_stride = (size_t)(backward ? Tin : M) * N * N;
     if (events && chunk < C) return fail(LCT_ERR_WORKSPACE, "stage events need a workspace for the whole batch");
+    if (minmax_keys) LCT_CUDA(cudaMemsetAsync(minmax_keys, 0xFF, (size_t)C * 2 * sizeof(unsigned long long), stream));
     const lct::ChainTables t = plan->tables();
     if (plan->groups > 1 && chunk >= C && C >= 2 && !events) {     // per-kernel events need the single-stream order
         // one batch: split the channels into groups, each an independent chain on its own stream
@@ -320,7 +322,8 @@ static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const 
             GpuLauncher lg{sg, plan->device};
             const int rc = lct::run_chain(lg, t, M, N, (int)(c1 - c0), D, Tin, tbe[0], be_dev, (int)c0,
                                           in + (size_t)c0 * in_stride, out + (size_t)c0 * out_stride,
-                                          s1 + (size_t)c0 * (M + 1) * N * N, s2 + (size_t)c0 * (M + 1) * 2 * N * N, backward);
+                                          s1 + (size_t)c0 * (M + 1) * N * N, s2 + (size_t)c0 * (M + 1) * 2 * N * N, backward,
+                                          lct::kStageAll, minmax_keys);
             if (rc < 0) return fail(LCT_ERR_UNSUPPORTED, "size not compiled");
             if (rc) return fail(LCT_ERR_CUDA, "kernel launch", lg.err);
             if (g) LCT_CUDA(cudaEventRecord(plan->join[g], sg));
@@ -333,7 +336,8 @@ static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const 
     for (long long c0 = 0; c0 < C; c0 += chunk) {
         const int cn = (int)((C - c0 < chunk) ? (C - c0) : chunk);
         const int rc = lct::run_chain(l, t, M, N, cn, D, Tin, tbe[0], be_dev, (int)c0,
-                                      in + (size_t)c0 * in_stride, out + (size_t)c0 * out_stride, s1, s2, backward);
+                                      in + (size_t)c0 * in_stride, out + (size_t)c0 * out_stride, s1, s2, backward,
+                                      lct::kStageAll, minmax_keys);
         if (rc < 0) return fail(LCT_ERR_UNSUPPORTED, "size not compiled");
         if (rc) return fail(LCT_ERR_CUDA, "kernel launch", l.err);
     }
@@ -349,6 +353,53 @@ int lct_forward(const lct_plan* plan, const float* x, const int32_t* tbe, const 
 int lct_backward(const lct_plan* plan, const float* gy, const int32_t* tbe, const int32_t* ten,
                  int32_t B, int32_t D, int32_t Tin, float* gx, void* ws, size_t ws_bytes, void* stream) {
     return run(plan, gy, tbe, ten, B, D, Tin, gx, ws, ws_bytes, stream, true);
+}
+
+int lct_forward_minmax(const lct_plan* plan, const float* x, const int32_t* tbe, const int32_t* ten,
+                       int32_t B, int32_t D, int32_t Tin, float* y, void* minmax_keys,
+                       void* ws, size_t ws_bytes, void* stream) {
+    if (!minmax_keys || ((uintptr_t)minmax_keys & 7)) return fail(LCT_ERR_INVALID, "bad minmax buffer");
+    return run(plan, x, tbe, ten, B, D, Tin, y, ws, ws_bytes, stream, false, nullptr,
+               static_cast<unsigned long long*>(minmax_keys));
+}
+
+static unsigned reduce_blocks(long long elems) {
+    long long b = (elems / 4 + 255) / 256;
+    return (unsigned)(b < 1 ? 1 : (b > 64 ? 64 : b));
+}
+
+int lct_minmax(const float* x, int32_t channels, int64_t elems, void* keys, void* stream_) {
+    if (!x || !keys || channels <= 0 || elems <= 0 || elems > 0xffffffffLL || ((uintptr_t)x & 15) || ((uintptr_t)keys & 7))
+        return fail(LCT_ERR_INVALID, "bad argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LCT_CUDA(cudaMemsetAsync(keys, 0xFF, (size_t)channels * 2 * sizeof(unsigned long long), stream));
+    lct::minmax_kernel<<<dim3(reduce_blocks(elems), channels), 256, 0, stream>>>(x, static_cast<unsigned long long*>(keys), elems);
+    LCT_CUDA(cudaGetLastError());
+    return LCT_OK;
+}
+
+int lct_normalize_feature(const float* x, const void* keys, float* out, int32_t channels, int64_t elems,
+                          float scale, void* stream_) {
+    if (!x || !keys || !out || channels <= 0 || elems <= 0 || (((uintptr_t)x | (uintptr_t)out) & 15))
+        return fail(LCT_ERR_INVALID, "bad argument");
+    lct::normalize_kernel<<<dim3(reduce_blocks(elems), channels), 256, 0, (cudaStream_t)stream_>>>(
+        x, out, static_cast<const unsigned long long*>(keys), elems, scale);
+    LCT_CUDA(cudaGetLastError());
+    return LCT_OK;
+}
+
+int lct_normalize_feature_backward(const float* x, const float* gout, const void* keys, float* gx, void* sums,
+                                   int32_t channels, int64_t elems, float scale, void* stream_) {
+    if (!x || !gout || !keys || !gx || !sums || channels <= 0 || elems <= 0) return fail(LCT_ERR_INVALID, "bad argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LCT_CUDA(cudaMemsetAsync(sums, 0, (size_t)channels * 2 * sizeof(double), stream));
+    const dim3 grid(reduce_blocks(elems), channels);
+    lct::normalize_bwd_sums_kernel<<<grid, 256, 0, stream>>>(x, gout, static_cast<const unsigned long long*>(keys),
+                                                             static_cast<double*>(sums), elems);
+    lct::normalize_bwd_kernel<<<grid, 256, 0, stream>>>(gout, gx, static_cast<const unsigned long long*>(keys),
+                                                        static_cast<const double*>(sums), elems, scale);
+    LCT_CUDA(cudaGetLastError());
+    return LCT_OK;
 }
 
 int lct_run_staged(const lct_plan* plan, const float* in, const int32_t* tbe, const int32_t* ten,

@@ -124,7 +124,8 @@ struct ChainTables {
 template <class Launcher>
 int run_chain(Launcher& l, const ChainTables& t, int M, int N, int C, int D, int Tin,
               int be_uniform, const int* be_dev, int c_base, const float* in, float* out,
-              float2* s1, float2* s2, bool backward, int mask = kStageAll) {
+              float2* s1, float2* s2, bool backward, int mask = kStageAll,
+              unsigned long long* minmax_keys = nullptr) {
     Params p{};
     p.M = M; p.N = N; p.C = C; p.D = D;
     p.s1 = s1; p.s2 = s2; p.filt = t.filt; p.conj_filter = backward ? 1 : 0;
@@ -169,6 +170,7 @@ int run_chain(Launcher& l, const ChainTables& t, int M, int N, int C, int D, int
         p.be_uniform = backward ? be_uniform : 0;
         p.be_dev = backward ? be_dev : nullptr;
         const BandTable& bt = backward ? t.mtxi_falloff : t.mtxi;
+        p.minmax_keys = backward ? nullptr : minmax_keys;
         p.ell = bt.ell; p.rowptr = bt.rowptr; p.vals = bt.vals;
         LCT_SWITCH_M(M, (launch_time_inv<kM>(p, l)));
         if (rc) return rc;

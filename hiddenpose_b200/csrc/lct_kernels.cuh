@@ -144,6 +144,12 @@ template <int LANES> LCT_DEV int line_thread(int tid) {
     else return tid / LANES;
 }
 
+#ifdef LCT_EMULATE
+static inline int float_bits(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+#else
+LCT_DEV int float_bits(float f) { return __float_as_int(f); }
+#endif
+
 struct Params {
     int M, N, C, D;
     // K1 input placement: rows [in_be, in_be+in_T) of the M-bin time axis come from `in`
@@ -165,13 +171,35 @@ struct Params {
     const float4* ell;
     const int* rowptr;
     const float* vals;
+    // optional (K5, forward): per-channel {min key, complemented max key} of the volume it writes, reduced
+    // with atomicMin while the values are still in registers (lct_normalize.cuh); pre-set to all ones
+    unsigned long long* minmax_keys;
 };
 
+// order-preserving key of a float and its position (see lct_normalize.cuh)
+LCT_DEV unsigned long long minmax_key(float v, unsigned int pos, bool is_max) {
+    const unsigned int b = (unsigned int)float_bits(v);
+    const unsigned int k = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return is_max ? ~(((unsigned long long)k << 32) | (0xffffffffu - pos)) : (((unsigned long long)k << 32) | pos);
+}
+LCT_DEV void minmax_commit(unsigned long long* keys, int c, unsigned long long kmin, unsigned long long kmax) {
 #ifdef LCT_EMULATE
-static inline int float_bits(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+    if (kmin < keys[2 * c]) keys[2 * c] = kmin;
+    if (kmax < keys[2 * c + 1]) keys[2 * c + 1] = kmax;
 #else
-LCT_DEV int float_bits(float f) { return __float_as_int(f); }
+    LCT_UNROLL
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, kmin, o), b = __shfl_xor_sync(0xffffffffu, kmax, o);
+        kmin = a < kmin ? a : kmin;
+        kmax = b < kmax ? b : kmax;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(keys + 2 * c, kmin);
+        atomicMin(keys + 2 * c + 1, kmax);
+    }
 #endif
+}
+
 
 // sum_e w[e] * src[(start + e) * stride] for one operator row; `src` must have two readable
 // (finite) rows past the last one, because short rows still touch three.
@@ -370,10 +398,27 @@ template <class P, int CT_> struct TimeInv {
             const size_t step = (size_t)P::TL * NN;
             const float* vc = vol + col;
             const float4* ell = reinterpret_cast<const float4*>(smem + kWork);
+            if (p.minmax_keys == nullptr) {
 #ifndef LCT_EMULATE
 #pragma unroll 4
 #endif
-            for (int j = tau; j < p.out_T; j += P::TL, d += step) *d = band_dot(p, ell, be + j, vc, CT);
+                for (int j = tau; j < p.out_T; j += P::TL, d += step) *d = band_dot(p, ell, be + j, vc, CT);
+            } else {
+                float mn = 3.4e38f, mx = -3.4e38f;
+                int jmn = 0, jmx = 0;
+#ifndef LCT_EMULATE
+#pragma unroll 4
+#endif
+                for (int j = tau; j < p.out_T; j += P::TL, d += step) {
+                    const float v = band_dot(p, ell, be + j, vc, CT);
+                    *d = v;
+                    if (v < mn) { mn = v; jmn = j; }
+                    if (v > mx) { mx = v; jmx = j; }
+                }
+                const unsigned int base = (unsigned int)(col0 + col);
+                minmax_commit(p.minmax_keys, p.c_base + c, minmax_key(mn, (unsigned int)jmn * NN + base, false),
+                              minmax_key(mx, (unsigned int)jmx * NN + base, true));
+            }
         }
     }
 };

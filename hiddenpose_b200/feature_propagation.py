@@ -41,13 +41,21 @@ class FeaturePropagation(nn.Module):
         assert mode == "lct", f"{mode} is not spported. Feature propagation only support lct by now"
         self.method = LCT(int(image_size), time_size, bin_len, wall_size, mode=mode, material=material)
         self.method.todev(dev, dnum)
+        self.method.fuse_minmax = True       # the caller's next op is normalize_feature (NlosPose.py:54)
 
     def forward(self, x, time_begin, time_end):
         return self.method(x, time_begin, time_end)
 
 
+def _native_normalize(x, scale):
+    from .lct_function import NormalizeFeatureFunction
+    return NormalizeFeatureFunction.apply(x.contiguous(), scale, getattr(x, "_lct_minmax", None))
+
+
 def normalize(data_bxcxdxhxw):
     """feature_propagation.py:260-270: per (b, c) min/max normalisation to [0, 1]."""
+    if data_bxcxdxhxw.is_cuda and data_bxcxdxhxw.dtype == torch.float32 and data_bxcxdxhxw.dim() == 5:
+        return _native_normalize(data_bxcxdxhxw, 1.0)
     b, c, d, h, w = data_bxcxdxhxw.shape
     flat = data_bxcxdxhxw.reshape(b, c, -1)
     shifted = flat - flat.min(2, keepdim=True)[0]
@@ -58,8 +66,11 @@ def normalize_feature(data_bxcxdxhxw):
     """feature_propagation.py:273-286: min/max normalisation times 10.
 
     The reference calls ``nn.ReLU()(x)`` and discards the result (line 274), so
-    negative LCT values do reach the ``min``; that behaviour is kept.
+    negative LCT values do reach the ``min``; that behaviour is kept.  CUDA float32 volumes go through
+    the library (``lct_normalize_feature``; the LCT layer hands over min/max it already reduced).
     """
+    if data_bxcxdxhxw.is_cuda and data_bxcxdxhxw.dtype == torch.float32 and data_bxcxdxhxw.dim() == 5:
+        return _native_normalize(data_bxcxdxhxw, 10.0)
     return normalize(data_bxcxdxhxw) * 10.0
 
 

@@ -52,6 +52,9 @@ class LctLayerBase(nn.Module):
         self._filter_half = ops.inverse_filter_half(self._N, self._M, self.width / self.trange, method, self.snr)
         self._lapw = ops.laplacian_filter() if method == "bp" else None       # tflct.py:73-77
         self._plan, self._dev, self.dnum = None, torch.device("cpu"), 2
+        # reduce the volume's per-channel min/max in the last kernel and leave them on the output for
+        # normalize_feature (FeaturePropagation turns this on: NlosPose.py:53-54 always normalises next)
+        self.fuse_minmax = False
         self._dense_cache = {}
 
     # -- reference attributes, materialised on demand --------------------------------
@@ -141,6 +144,10 @@ class LctLayerBase(nn.Module):
         if feture_bxdxtxhxw.device != self._plan.device:
             raise RuntimeError(f"input is on {feture_bxdxtxhxw.device} but the layer was moved to {self._plan.device}")
         x = feture_bxdxtxhxw.contiguous().float()
+        if self.fuse_minmax and self._lapw is None:
+            y, keys = LctFunction.apply(x, self._plan, tbes, tens, True)
+            y._lct_minmax = (keys, y._version, y.data_ptr())
+            return y
         return LctFunction.apply(x, self._plan, tbes, tens)
 
     @staticmethod

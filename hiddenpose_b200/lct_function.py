@@ -70,12 +70,21 @@ class LctPlan:
         _native.check(fn(self.handle, src.data_ptr(), _i32_array(tbes), _i32_array(tens), B, D, Tin,
                          dst.data_ptr(), ws.data_ptr(), nbytes, stream))
 
-    def forward(self, x, tbes, tens):
+    def forward(self, x, tbes, tens, want_minmax=False):
+        """Returns the volume, and -- if asked -- the per-channel {min, max} keys the last kernel reduced
+        while writing it (consumed by normalize_feature; see include/hiddenpose_lct.h)."""
         B, D, Tin, H, W = x.shape
         y = torch.empty((B, D, self.M, H, W), dtype=torch.float32, device=x.device)
         with torch.cuda.device(self.device):
-            self._run(self.lib.lct_forward, x, tbes, tens, B, D, Tin, y)
-        return y
+            if not want_minmax:
+                self._run(self.lib.lct_forward, x, tbes, tens, B, D, Tin, y)
+                return y
+            keys = torch.empty((B * D, 2), dtype=torch.int64, device=x.device)
+            ws, nbytes = self.workspace(B * D)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _native.check(self.lib.lct_forward_minmax(self.handle, x.data_ptr(), _i32_array(tbes), _i32_array(tens),
+                                                      B, D, Tin, y.data_ptr(), keys.data_ptr(), ws.data_ptr(), nbytes, stream))
+        return y, keys
 
     def backward(self, gy, tbes, tens, Tin):
         B, D, M, H, W = gy.shape
@@ -122,19 +131,62 @@ class LctPlan:
 
 class LctFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, plan, tbes, tens):
+    def forward(ctx, x, plan, tbes, tens, want_minmax=False):
         ctx.plan, ctx.tbes, ctx.tens, ctx.tin = plan, tuple(tbes), tuple(tens), x.shape[2]
+        if want_minmax and plan.lapw is None:
+            y, keys = plan.forward(x, tbes, tens, want_minmax=True)
+            ctx.mark_non_differentiable(keys)
+            return y, keys
         y = plan.forward(x, tbes, tens)
         if plan.lapw is not None:                       # method == 'bp' (tflct.py:164-175)
             y = plan.laplacian(y, adjoint=False)
         return y
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, *unused):
         if not ctx.needs_input_grad[0]:
-            return None, None, None, None
+            return None, None, None, None, None
         plan = ctx.plan
         gy = gy.contiguous().float()
         if plan.lapw is not None:
             gy = plan.laplacian(gy, adjoint=True)
-        return plan.backward(gy, ctx.tbes, ctx.tens, ctx.tin), None, None, None
+        return plan.backward(gy, ctx.tbes, ctx.tens, ctx.tin), None, None, None, None
+
+
+class NormalizeFeatureFunction(torch.autograd.Function):
+    """feature_propagation.py:260-286 on the CUDA library: ``(x - min) / (max(x - min) + 1e-15) * scale`` per
+    (batch, channel) volume, forward and backward.  ``hint`` = (keys, version, data_ptr) left on the LCT output
+    by the layer when its last kernel already reduced min / max; otherwise one reduction pass finds them."""
+
+    @staticmethod
+    def forward(ctx, x, scale, hint):
+        lib = _native.load()
+        b, c = x.shape[0], x.shape[1]
+        elems = x.numel() // (b * c)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        with torch.cuda.device(x.device):
+            if hint is not None and hint[1] == x._version and hint[2] == x.data_ptr() and hint[0].shape[0] == b * c:
+                keys = hint[0]
+            else:
+                keys = torch.empty((b * c, 2), dtype=torch.int64, device=x.device)
+                _native.check(lib.lct_minmax(x.data_ptr(), b * c, elems, keys.data_ptr(), stream))
+            out = torch.empty_like(x)
+            _native.check(lib.lct_normalize_feature(x.data_ptr(), keys.data_ptr(), out.data_ptr(), b * c, elems, float(scale), stream))
+        ctx.save_for_backward(x, keys)
+        ctx.scale = float(scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, keys = ctx.saved_tensors
+        lib = _native.load()
+        b, c = x.shape[0], x.shape[1]
+        elems = x.numel() // (b * c)
+        gout = gout.contiguous().float()
+        gx = torch.empty_like(x)
+        sums = torch.empty((b * c, 2), dtype=torch.float64, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        with torch.cuda.device(x.device):
+            _native.check(lib.lct_normalize_feature_backward(x.data_ptr(), gout.data_ptr(), keys.data_ptr(), gx.data_ptr(),
+                                                             sums.data_ptr(), b * c, elems, ctx.scale, stream))
+        return gx, None, None

@@ -14,6 +14,8 @@
  *                         explicit backward; it is the adjoint of the same linear chain,
  *                         SURVEY.md section 3.5)
  *   lct_bp_laplacian   <- the method=='bp' tail             models/tflct.py:164-175
+ *   lct_normalize_feature[_backward], lct_minmax, lct_forward_minmax
+ *                      <- normalize_feature                 models/feature_propagation.py:273-286
  *
  * Plain C types only: pointers, sizes, integer return codes (0 = success).  Nothing
  * throws across this boundary.  Device pointers are raw CUDA device addresses; `stream`
@@ -93,6 +95,23 @@ int lct_forward(const lct_plan* plan, const float* x, const int32_t* tbe, const 
 int lct_backward(const lct_plan* plan, const float* gy, const int32_t* tbe, const int32_t* ten,
                  int32_t B, int32_t D, int32_t Tin, float* gx,
                  void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * normalize_feature, the op NlosPose applies to the LCT volume (models/feature_propagation.py:273-286,
+ * NlosPose.py:54):  out = (x - min) / (max(x - min) + 1e-15) * scale  per channel of `elems` values.
+ * min / max travel as two 64-bit keys per channel ({value, position}, device memory, 16 bytes per
+ * channel).  lct_forward_minmax is lct_forward that also reduces the keys of the volume it writes
+ * (in its last kernel, while the values are in registers); lct_minmax computes them for any tensor.
+ * The backward pass needs `sums`: 16 bytes of device scratch per channel.
+ */
+int lct_forward_minmax(const lct_plan* plan, const float* x, const int32_t* tbe, const int32_t* ten,
+                       int32_t B, int32_t D, int32_t Tin, float* y, void* minmax_keys,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int lct_minmax(const float* x, int32_t channels, int64_t elems, void* minmax_keys, void* stream);
+int lct_normalize_feature(const float* x, const void* minmax_keys, float* out, int32_t channels, int64_t elems,
+                          float scale, void* stream);
+int lct_normalize_feature_backward(const float* x, const float* gout, const void* minmax_keys, float* gx,
+                                   void* sums, int32_t channels, int64_t elems, float scale, void* stream);
 
 /*
  * Measurement hook: lct_forward (backward == 0) or lct_backward (backward != 0) with six

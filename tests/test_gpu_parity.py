@@ -187,3 +187,45 @@ def test_streamer_matches_batch_by_batch():
     hp.LctStreamer(layer, [0] * B, [M] * B, depth=2).run(xs, ys)
     for xh, yh in zip(xs, ys):
         assert torch.equal(yh, layer(xh.cuda(), [0] * B, [M] * B).cpu())
+
+
+def _ref_normalize_feature(x):
+    """feature_propagation.py:273-286, the reference's own op sequence (torch)."""
+    b, c, d, h, w = x.shape
+    k = x.reshape(b, c, -1)
+    z = k - k.min(2, keepdim=True)[0]
+    n = z / (z.max(2, keepdim=True)[0] + 1e-15)
+    n = n * 10.
+    return n.view(b, c, d, h, w)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_normalize_feature_forward_backward(fused):
+    """normalize_feature on the library (row f1): bit-identical forward, gradient vs autograd of the
+    reference expression; with min/max handed over by the LCT's last kernel and with the stand-alone pass."""
+    import hiddenpose_b200 as hp
+    M, N, B = 64, 16, 3
+    fp = hp.FeaturePropagation(time_size=M, image_size=N, bin_len=0.08, dnum=1, dev=0)
+    x = torch.rand(B, 1, M, N, N, device="cuda")
+    y = fp(x, [0] * 3, [M] * 3)
+    assert hasattr(y, "_lct_minmax")
+    if not fused:
+        y = y.clone()                                    # drops the hint: stand-alone reduction pass
+    yl = y.detach().clone().requires_grad_(True)
+    if fused:
+        yl._lct_minmax = (y._lct_minmax[0], yl._version, yl.data_ptr())
+        # the keys describe the same values, only the tensor identity differs
+    out = hp.normalize_feature(yl)
+    ref_in = y.detach().clone().requires_grad_(True)
+    ref = _ref_normalize_feature(ref_in)
+    assert torch.equal(out, ref)
+    g = torch.randn_like(out)
+    out.backward(g)
+    ref.backward(g)
+    assert O.rel_l2(yl.grad.cpu(), ref_in.grad.cpu()) <= 1e-5
+    # keys reduced inside the LCT kernel equal the stand-alone reduction
+    if fused:
+        mn = y.detach().reshape(B, -1).min(1)[0]
+        z = hp.normalize_feature(y.detach().clone())      # no hint -> lct_minmax path
+        assert torch.equal(z, out.detach())
+        assert float(mn.min()) < 0                       # negatives do reach the min (reference quirk C8)
