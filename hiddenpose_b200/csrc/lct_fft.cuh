@@ -41,12 +41,16 @@ constexpr int kTwN = 1024;   // size of the master twiddle table exp(-2*pi*i*j/1
 #define LCT_PACKED_FP32 1
 LCT_DEV float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
 LCT_DEV float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+// a*b = a * b.x + (-a.y*b.y, a.x*b.y): FMUL2 on the swapped pair with b.y broadcast, then FFMA2 with b.x
+// broadcast and a per-half sign on the addend -- two instructions, all swizzles/signs are operand modifiers
 LCT_DEV float2 cmul(float2 a, float2 b) {
-    return __ffma2_rn(make_float2(a.x, a.x), b, __fmul2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x)));
+    const float2 u = __fmul2_rn(make_float2(a.y, a.x), make_float2(b.y, b.y));
+    return __ffma2_rn(a, make_float2(b.x, b.x), make_float2(-u.x, u.y));
 }
 // a * conj(b)
 LCT_DEV float2 cmulc(float2 a, float2 b) {
-    return __ffma2_rn(make_float2(a.x, a.x), make_float2(b.x, -b.y), __fmul2_rn(make_float2(a.y, a.y), make_float2(b.y, b.x)));
+    const float2 u = __fmul2_rn(make_float2(a.y, a.x), make_float2(b.y, b.y));
+    return __ffma2_rn(a, make_float2(b.x, b.x), make_float2(u.x, -u.y));
 }
 LCT_DEV float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
 #else
@@ -57,6 +61,9 @@ LCT_DEV float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b
 LCT_DEV float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
 LCT_DEV float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 #endif
+// scalar forms (2 FMUL + 2 FFMA), for code where the packed form's register pairing costs more than it saves
+LCT_DEV float2 cmul_s(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+LCT_DEV float2 cmulc_s(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
 LCT_DEV float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 // multiply by -i (forward) / +i (inverse)
 template <bool INV> LCT_DEV float2 mul_mi(float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
@@ -107,8 +114,7 @@ template <bool INV> LCT_DEV float2 twmul32(float2 a, int idx) {
     }
     if (INV) ss = -ss;
 #ifdef LCT_PACKED_FP32
-    // (x*cc + y*ss, y*cc - x*ss) = x*(cc, -ss) + y*(ss, cc)
-    return __ffma2_rn(make_float2(a.x, a.x), make_float2(cc, -ss), __fmul2_rn(make_float2(a.y, a.y), make_float2(ss, cc)));
+    return cmul(a, make_float2(cc, -ss));            // a * (cc - i ss)
 #else
     return make_float2(a.x * cc + a.y * ss, a.y * cc - a.x * ss);
 #endif

@@ -47,8 +47,9 @@ __constant__ float2 c_tw[kTwN];          // exp(-2*pi*i*j/1024), built in double
 __device__ float2 g_tw[kTwN];            // same table in global memory for lane-divergent lookups
 struct TwConst {
     static LCT_DEV float2 get(int i) { return c_tw[i]; }
-    static LCT_DEV float2 mul(float2 a, int i) { return cmul(a, get(i)); }      // a * w^i
-    static LCT_DEV float2 mulc(float2 a, int i) { return cmulc(a, get(i)); }    // a * conj(w^i)
+    // scalar multiplies here: in the time kernels the packed form measured slower (register pairing)
+    static LCT_DEV float2 mul(float2 a, int i) { return cmul_s(a, get(i)); }      // a * w^i
+    static LCT_DEV float2 mulc(float2 a, int i) { return cmulc_s(a, get(i)); }    // a * conj(w^i)
     template <int Ls, int STR> static LCT_DEV float2 stage_mul(float2 a, int k, int lo) { return mul(a, (k * lo) * (kTwN / Ls)); }
     template <int Ls, int STR> static LCT_DEV float2 stage_mulc(float2 a, int k, int lo) { return mulc(a, (k * lo) * (kTwN / Ls)); }
 };
@@ -293,7 +294,7 @@ template <class P, int CT_> struct TimeFwd {
                 const float2 ev = cscale(cadd(zk, zm), 0.5f);
                 const float2 d = csub(zk, zm);
                 const float2 od = make_float2(0.5f * d.y, -0.5f * d.x);
-                const float2 t = cmul(od, TwS::get(k * (kTwN / (2 * M))));
+                const float2 t = TwS::mul(od, k * (kTwN / (2 * M)));
                 *lo = cadd(ev, t);
                 if (hi != lo) *hi = cconj(csub(ev, t));
             };
@@ -364,7 +365,7 @@ template <class P, int CT_> struct TimeInv {
             auto z_at = [&](int k) -> float2 {
                 const float2 xk = zs[k * CT + col];
                 const float2 xm = cconj(zs[(M - k) * CT + col]);
-                const float2 d = cmulc(csub(xk, xm), TwS::get(k * (kTwN / (2 * M))));
+                const float2 d = TwS::mulc(csub(xk, xm), k * (kTwN / (2 * M)));
                 return cadd(cadd(xk, xm), make_float2(-d.y, d.x));
             };
             if constexpr (SL == 0) {
