@@ -290,6 +290,57 @@ LCT_DEV void inv_stage(int tau, LD ld, ST stf) {
     }
 }
 
+// Variants of the two stage functions that take the inter-stage twiddles from a caller-held array
+// (tw[m*(r-1) + k-1] = w_Ls^(k lo) for butterfly m, filled once by load_stage_twiddles) so that
+// several transforms with the same thread mapping share one set of table reads.
+template <class P, int s, class TW> LCT_DEV void load_stage_twiddles(int tau, float2* tw) {
+    constexpr int r = P::radix(s), Ls = P::Ls(s), str = P::st(s), NB = P::L / r;
+    LCT_UNROLL
+    for (int m = 0; m < NB / P::TL; ++m) {
+        const int lo = (tau + m * P::TL) % str;
+        LCT_UNROLL
+        for (int k = 1; k < r; ++k) tw[m * (r - 1) + k - 1] = TW::get((k * lo) * (kTwN / Ls));
+    }
+}
+template <class P, int s> struct StageTwiddles { static constexpr int kCount = (P::L / P::radix(s) / P::TL) * (P::radix(s) - 1); };
+
+template <class P, int s, class LD, class ST>
+LCT_DEV void fwd_stage_tw(int tau, const float2* tw, LD ld, ST stf) {
+    constexpr int r = P::radix(s), Ls = P::Ls(s), str = P::st(s), NB = P::L / r;
+    static_assert(s < P::S - 1, "the last stage has no twiddles");
+    LCT_UNROLL
+    for (int m = 0; m < NB / P::TL; ++m) {
+        const int b = tau + m * P::TL;
+        const int base = (b / str) * Ls + (b % str);
+        float2 a[r];
+        LCT_UNROLL
+        for (int q = 0; q < r; ++q) a[q] = ld(base + q * str, m * r + q);
+        dft<r, false>(a);
+        LCT_UNROLL
+        for (int k = 1; k < r; ++k) a[k] = cmul(a[k], tw[m * (r - 1) + k - 1]);
+        LCT_UNROLL
+        for (int k = 0; k < r; ++k) stf(base + k * str, m * r + k, a[k]);
+    }
+}
+template <class P, int s, class LD, class ST>
+LCT_DEV void inv_stage_tw(int tau, const float2* tw, LD ld, ST stf) {
+    constexpr int r = P::radix(s), Ls = P::Ls(s), str = P::st(s), NB = P::L / r;
+    static_assert(s < P::S - 1, "the last stage has no twiddles");
+    LCT_UNROLL
+    for (int m = 0; m < NB / P::TL; ++m) {
+        const int b = tau + m * P::TL;
+        const int base = (b / str) * Ls + (b % str);
+        float2 a[r];
+        LCT_UNROLL
+        for (int k = 0; k < r; ++k) a[k] = ld(base + k * str, m * r + k);
+        LCT_UNROLL
+        for (int k = 1; k < r; ++k) a[k] = cmulc(a[k], tw[m * (r - 1) + k - 1]);
+        dft<r, true>(a);
+        LCT_UNROLL
+        for (int q = 0; q < r; ++q) stf(base + q * str, m * r + q, a[q]);
+    }
+}
+
 // Visit (pos, slot) of every element this thread owns in stage s
 // (all r per butterfly, or only the lower half).
 template <class P, int s, class FN> LCT_DEV void for_each_slot(int tau, FN fn) {

@@ -667,12 +667,13 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
             float2* Tr = T + row * RS;
             float2* Xr = X + rl * RS;
             if constexpr (st3 == 0) {
-                float2 in[EW];
+                float2 in[EW], tw[StageTwiddles<PWp, 0>::kCount];
+                load_stage_twiddles<PWp, 0, TwP>(tau, tw);              // shared by both parities
                 for_each_slot<PWp, 0>(tau, [&](int pos, int slot) { in[slot] = Tr[pos]; });
-                fwd_stage<PWp, 0, false, TwP>(tau,
+                fwd_stage_tw<PWp, 0>(tau, tw,
                     [&](int, int slot) { return in[slot]; },
                     [&](int pos, int, float2 v) { Tr[pos] = v; });
-                fwd_stage<PWp, 0, false, TwP>(tau,
+                fwd_stage_tw<PWp, 0>(tau, tw,
                     [&](int pos, int slot) { return TwP::mul(in[slot], pos * (kTwN / L)); },
                     [&](int pos, int, float2 v) { Xr[pos] = v; });
 #if !defined(LCT_EMULATE) && defined(LCT_PLANE_PREFETCH)
@@ -706,11 +707,12 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
                     [&](int, int slot) { return b[slot]; },
                     [&](int pos, int, float2 v) { Xr[pos] = v; });
             } else {
-                float2 ya[EW];
-                inv_stage<PWp, 0, false, TwP>(tau,
+                float2 ya[EW], tw[StageTwiddles<PWp, 0>::kCount];
+                load_stage_twiddles<PWp, 0, TwP>(tau, tw);
+                inv_stage_tw<PWp, 0>(tau, tw,
                     [&](int pos, int) { return Tr[pos]; },
                     [&](int, int slot, float2 v) { ya[slot] = v; });
-                inv_stage<PWp, 0, false, TwP>(tau,
+                inv_stage_tw<PWp, 0>(tau, tw,
                     [&](int pos, int) { return Xr[pos]; },
                     [&](int pos, int slot, float2 v) {
                         Tr[pos] = cadd(ya[slot], TwP::mulc(v, pos * (kTwN / L)));
