@@ -229,3 +229,18 @@ def test_normalize_feature_forward_backward(fused):
         z = hp.normalize_feature(y.detach().clone())      # no hint -> lct_minmax path
         assert torch.equal(z, out.detach())
         assert float(mn.min()) < 0                       # negatives do reach the min (reference quirk C8)
+
+
+def test_stream_groups_do_not_change_results(monkeypatch):
+    """The two-stream channel split (default) returns the same bits as the single-stream order."""
+    import hiddenpose_b200 as hp
+    M, N, B = 64, 32, 5
+    x = torch.rand(B, 1, M, N, N, device="cuda")
+    outs = []
+    for groups in ("1", "2", "3"):
+        monkeypatch.setenv("LCT_STREAM_GROUPS", groups)
+        layer = hp.lct(spatial=N, crop=M, bin_len=0.08)
+        layer.todev("cuda:0", 1)
+        outs.append(layer(x, [0] * B, [M] * B))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
