@@ -35,10 +35,7 @@ template <> struct LinePlan<256> { using type = Plan<16, 16>; };
 template <> struct LinePlan<512> { using type = Plan<32, 16>; };
 
 // column tile (in columns of the flattened H*W axis) for the T-axis kernels
-#ifndef LCT_TIME_CT
-#define LCT_TIME_CT 32
-#endif
-template <int M> struct TimeTile { static constexpr int CT = (M >= 512) ? 16 : LCT_TIME_CT; };
+template <int M> struct TimeTile { static constexpr int CT = (M >= 512) ? 16 : 32; };     // 16-wide tiles measured slower below M = 512
 // column tile along W for the H-axis kernels
 template <int N> struct RowTile { static constexpr int CT = (N >= 256) ? 16 : (N < 32 ? N : 32); };
 // rows per block for K3
@@ -49,13 +46,11 @@ template <int N> struct LineRows {
 
 // plane-resident fusion of K2+K3+K4: the 2N x (N+1) c64 plane must fit in shared memory
 constexpr bool plane_fusable(int N) { return N <= 64; }
-#ifndef LCT_PLANE_THREADS
-#define LCT_PLANE_THREADS 512
-#endif
+constexpr int kPlaneThreads = 512;          // 256-thread blocks (3 per SM) measured slower
 template <int N> struct PlaneKernel {
     using PHp = typename ColPlan<2 * N>::type;
     static constexpr int kFull = N * PHp::TL;                               // one column batch
-    static constexpr int NT = kFull < LCT_PLANE_THREADS ? kFull : LCT_PLANE_THREADS;
+    static constexpr int NT = kFull < kPlaneThreads ? kFull : kPlaneThreads;
     using type = PlaneFilter<PHp, typename ColPlan<N>::type, NT>;
 };
 // H-frequency held by plane row r after the forward H stages (the fused filter is stored in this order)

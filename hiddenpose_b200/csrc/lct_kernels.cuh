@@ -1,21 +1,24 @@
-// The five LCT kernels (sm_100a), written as sequences of barrier-separated
-// phases so that the very same code can be stepped thread by thread on the CPU
-// by tests/emu (LCT_EMULATE; test infrastructure only, never a product path).
+// The LCT kernels (sm_100a), written as sequences of barrier-separated phases so that the very
+// same code can be stepped thread by thread on the CPU by tests/emu (LCT_EMULATE; test
+// infrastructure only, never a product path).
 //
 // Data flow for C = B*D channels, M time bins, N x N spatial grid
 // (reference: /root/reference/models/tflct.py:94-179):
 //
 //   K1 TimeFwd   x (C,Tin,N,N) f32 -> S1 (C,M+1,N,N) c64
 //                time window (tflct.py:104-110), falloff (:123-127), sqrt(t)
-//                resample as a CSR gather (:135-138), zero-extend to 2M (:140)
+//                resample as a banded gather (:135-138), zero-extend to 2M (:140)
 //                and real FFT along T (first axis of :144), half spectrum.
 //   K2 RowFwd    S1 -> S2 (C,M+1,2N,N): zero-extended FFT along H (:144).
 //   K3 ColFilter S2 in place: zero-extended FFT along W, Wiener multiply
 //                (:145-150), inverse FFT along W, crop to N (:151,153).
 //   K4 RowInv    S2 -> S1 (C,M+1,N,N): inverse FFT along H, crop (:151,153).
 //   K5 TimeInv   S1 -> y (C,Tout,N,N) f32: Hermitian inverse FFT along T, crop
-//                to M, real part (:153), inverse resample mtxi as a CSR gather
-//                (:156-159) [+ falloff and window crop for the backward pass].
+//                to M, real part (:153), inverse resample mtxi as a banded gather
+//                (:156-159) [+ falloff and window crop for the backward pass]; optionally
+//                reduces the volume's per-channel min/max for normalize_feature.
+//   PlaneFilter  K2 + K3 + K4 in one kernel with the (c, kt) plane resident in shared memory;
+//                used whenever the plane fits (N <= 64).
 //
 // The backward pass is the same chain with conj(filter), the falloff moved
 // from K1's input to K5's output and the window cut out at the end
@@ -605,35 +608,22 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
     static_assert(L % RBt == 0, "row batches must tile the plane");
     static constexpr int nWB = L / RBt;
     static constexpr int RS = N + 1;
-#ifdef LCT_PLANE_TW_CONST
-    using TwP = TwConst;
-    static constexpr size_t kTwBytes = 0;
-#else
     using TwP = TwShared<L>;
     static constexpr size_t kTwBytes = TwP::kBytes;
-#endif
     // plane T[L][RS] + side buffer X[RBt][RS]: the odd-parity transform of a row batch is exchanged
     // through X while the even one uses the rows' own slots, so both run in the same three phases
     static constexpr size_t kSmem = kTwBytes + (size_t)(L + RBt) * RS * sizeof(float2);
     static constexpr int kPhases = 2 + nWB * 3 + 2;
     static constexpr int EW = PWp::E;
     static constexpr bool kWarpSync = false;
-#ifndef LCT_PLANE_MINBLOCKS
-#define LCT_PLANE_MINBLOCKS 2
-#endif
-#ifndef LCT_NO_PLANE_PREFETCH
-#define LCT_PLANE_PREFETCH 1
-#endif
-    static constexpr int kMinBlocks = (LCT_PLANE_MINBLOCKS * kSmem <= 220 * 1024) ? LCT_PLANE_MINBLOCKS : 1;
+    static constexpr int kMinBlocks = (2 * kSmem <= 220 * 1024) ? 2 : 1;      // two blocks per SM at <= 64 registers
     struct Regs {};
     static void grid(const Params& p, int& gx, int& gy) { gx = p.C; gy = p.M + 1; }   // c fastest: filter plane reused from L2
     static int iterations(const Params&) { return 1; }
 
     static constexpr bool kHasPrologue = true;
     static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) {
-#ifndef LCT_PLANE_TW_CONST
         TwP::fill(smem, tid, kThreads);
-#endif
     }
 
     template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem, int tid, int bx, int by, int) {
@@ -676,7 +666,7 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
                 fwd_stage_tw<PWp, 0>(tau, tw,
                     [&](int pos, int slot) { return TwP::mul(in[slot], pos * (kTwN / L)); },
                     [&](int pos, int, float2 v) { Xr[pos] = v; });
-#if !defined(LCT_EMULATE) && defined(LCT_PLANE_PREFETCH)
+#ifndef LCT_EMULATE
                 {   // pull next phase's filter values from L2 towards L1 while the exchange settles
                     const float4* f = reinterpret_cast<const float4*>(p.filt) + (size_t)kt * N * L + row;
                     for_each_slot<PWp, 1>(tau, [&](int pos, int) {

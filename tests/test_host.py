@@ -93,7 +93,6 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+(oracle|tests)\b", src, re.M), f
-                assert "/root/reference" not in src.replace("/root/reference/models", "").replace("/root/reference/utils", "") or True
 
 
 def test_normalize_feature_keeps_negative_minimum():
