@@ -122,12 +122,16 @@ def inverse_filter_half(N: int, M: int, slope: float, method: str = "lct", snr: 
     z, y, x, val = psf_support(N, M, slope)
     out = np.empty((M + 1, 2 * N, 2 * N), dtype=np.complex64)
     flat = (y * (2 * N) + x).astype(np.int64)
+    unique = len(np.unique(flat)) == len(flat)              # several z per (y, x) only on exact ties
+    phase_table = np.exp((-2j * np.pi / (2 * M)) * np.arange(2 * M)) * float(val)      # built in double
     for k0 in range(0, M + 1, planes_per_chunk):
         kt = np.arange(k0, min(M + 1, k0 + planes_per_chunk))
-        phase = np.exp((-2j * np.pi / (2 * M)) * ((kt[:, None] * z[None, :]) % (2 * M)))
+        phase = phase_table[(kt[:, None] * z[None, :]) % (2 * M)]
         plane = np.zeros((len(kt), 4 * N * N), dtype=np.complex128)
-        # several z per (y, x) happen on exact ties, so accumulate
-        np.add.at(plane, (slice(None), flat), phase * float(val))
+        if unique:
+            plane[:, flat] = phase
+        else:
+            np.add.at(plane, (slice(None), flat), phase)
         f = sfft.fft2(plane.reshape(len(kt), 2 * N, 2 * N), axes=(1, 2), workers=-1)
         if method == "lct":
             w = np.conj(f) / (1.0 / snr + f.real ** 2 + f.imag ** 2)        # tflct.py:60
