@@ -244,3 +244,28 @@ def test_stream_groups_do_not_change_results(monkeypatch):
         outs.append(layer(x, [0] * B, [M] * B))
     torch.cuda.synchronize()
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+_SIZES = [(M, N) for M in (32, 64, 128, 256, 512) for N in (8, 16, 32, 64, 128, 256) if M * N * N <= (1 << 21)]
+
+
+@pytest.mark.parametrize("M,N", _SIZES)
+def test_every_compiled_size_forward_backward(M, N):
+    """Every (time_bins, spatial) instantiation the library compiles, forward and backward, with a
+    partial window and two channels, against the oracle's op sequence (run with torch's CUDA FFT for
+    speed: test-only; the volumes are too many for the CPU oracle in one suite)."""
+    bl = 0.01 * 512 / M
+    layer = _layer(N, M, bl, 2)
+    orc = O.LctOracle(N, M, bl)
+    gen = torch.Generator(device="cuda").manual_seed(M * 1000 + N)
+    tin = M - 3
+    x = torch.rand(1, 2, tin, N, N, device="cuda", generator=gen)
+    g = torch.randn(1, 2, M, N, N, device="cuda", generator=gen)
+    xd = x.clone().requires_grad_(True)
+    y = layer(xd, [2], [2 + tin])
+    y.backward(g)
+    xo = x.clone().requires_grad_(True)
+    yo = orc.forward(xo, [2], [2 + tin])
+    yo.backward(g)
+    assert O.rel_l2(y.detach().cpu(), yo.detach().cpu()) <= TOL_Y
+    assert O.rel_l2(xd.grad.cpu(), xo.grad.cpu()) <= TOL_G
