@@ -267,6 +267,8 @@ def main():
     # ---- end to end: pinned host input -> H2D -> forward -> D2H of the volume, every step ---
     # through the public streaming API (hiddenpose_b200.LctStreamer): consecutive steps overlap
     # their upload / transform / download legs; every step still moves its own input and output.
+    from hiddenpose_b200.streaming import bind_host_to_gpu
+    numa_bound = bind_host_to_gpu(local_rank)          # pinned buffers on the GPU's own NUMA node
     n_buf = 4
     x_hosts = [x.cpu().pin_memory() for _ in range(n_buf)]
     y_hosts = [torch.empty(B, 1, M, N, N).pin_memory() for _ in range(n_buf)]
@@ -322,7 +324,8 @@ def main():
                     "matches_device_path": e2e_ok,
                     "how": "LctStreamer public API: pinned x -> H2D -> lct.forward -> D2H of the whole volume for every "
                            "step; upload/transform/download of consecutive steps overlap on three streams; host wall "
-                           "clock from first upload to last byte landed"},
+                           "clock from first upload to last byte landed; median of 3 runs of K steps",
+                    "runs_ms": e2e_runs, "host_bound_to_gpu_numa_node": numa_bound},
             "gpu_launches": n_kernels * K,
             "fwd_bwd": {"value": world * B * K / (fb_ms * 1e-3), "unit": "transients/s", "ms_per_step": fb_ms / K,
                         "gpu_launches": 2 * n_kernels * K},

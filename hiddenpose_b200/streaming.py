@@ -12,6 +12,28 @@ from __future__ import annotations
 import torch
 
 
+def bind_host_to_gpu(device_index: int) -> bool:
+    """Pins the calling process to the CPU cores NVML reports as local to the GPU, so that the pinned
+    host buffers allocated afterwards (first touch) sit on the GPU's own NUMA node and its PCIe root
+    port.  Returns False when NVML or the affinity call is unavailable (nothing is changed then)."""
+    try:
+        import math
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = math.ceil((os.cpu_count() or 1) / 64)
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
+
+
 class LctStreamer:
     """Pipelines ``(x_host) -> layer -> (y_host)`` over pinned host buffers.
 
