@@ -269,3 +269,23 @@ def test_every_compiled_size_forward_backward(M, N):
     yo.backward(g)
     assert O.rel_l2(y.detach().cpu(), yo.detach().cpu()) <= TOL_Y
     assert O.rel_l2(xd.grad.cpu(), xo.grad.cpu()) <= TOL_G
+
+
+def test_cuda_graph_capture_replays_the_layer():
+    """The whole forward (two internal streams, no allocation or sync inside the library) can be captured
+    in a CUDA graph and replayed on new data -- what a launch-bound caller with tiny batches would do."""
+    M, N, B = 64, 16, 2
+    layer = _layer(N, M, 0.08, 1)
+    static_x = torch.rand(B, 1, M, N, N, device="cuda")
+    with torch.no_grad():
+        layer(static_x, [0] * B, [M] * B)                       # warm up outside the capture
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_y = layer(static_x, [0] * B, [M] * B)
+        for _ in range(2):
+            fresh = torch.rand_like(static_x)
+            static_x.copy_(fresh)
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(static_y, layer(fresh, [0] * B, [M] * B))
