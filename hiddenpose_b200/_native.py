@@ -37,6 +37,8 @@ class LctDesc(ctypes.Structure):
         ("mtx_rowptr", ctypes.POINTER(ctypes.c_int32)), ("mtx_colidx", ctypes.POINTER(ctypes.c_int32)),
         ("mtx_vals", ctypes.POINTER(ctypes.c_float)), ("falloff", ctypes.POINTER(ctypes.c_float)),
         ("filter_half", ctypes.POINTER(ctypes.c_float)),
+        ("psf_z", ctypes.POINTER(ctypes.c_int32)), ("psf_yx", ctypes.POINTER(ctypes.c_int32)),
+        ("psf_count", ctypes.c_int32), ("psf_value", ctypes.c_float), ("snr", ctypes.c_float), ("method_bp", ctypes.c_int32),
     ]
 
 

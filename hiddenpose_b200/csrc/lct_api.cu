@@ -13,6 +13,7 @@
 
 #include "hiddenpose_lct.h"
 #include "lct_chain.cuh"
+#include "lct_filter_build.cuh"
 #include "lct_normalize.cuh"
 #include "lct_stencil.cuh"
 #include "lct_tables.h"
@@ -119,6 +120,46 @@ __global__ void scale_filter_kernel(float2* f, size_t n, float s) {
 
 }  // namespace
 
+// Builds the scaled filter on the device from the PSF support (lct_filter_build.cuh).
+template <int N>
+int build_filter_on_device(const lct_desc* d, float2* out, bool fused, float scale) {
+    using PH = typename lct::ColPlan<2 * N>::type;
+    using PL = typename lct::LinePlan<2 * N>::type;
+    constexpr int L = 2 * N, CT = (L >= 512) ? 16 : (L < 32 ? L : 32), RB = lct::LineRows<N>::RB;
+    const int M = d->time_bins;
+    const size_t nfilt = (size_t)(M + 1) * L * L;
+    float2* planes = nullptr;
+    int *dz = nullptr, *dyx = nullptr;
+    auto cleanup = [&]() { cudaFree(planes); cudaFree(dz); cudaFree(dyx); };
+#define LCT_TRYC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(LCT_ERR_CUDA, #call, e_); } } while (0)
+    LCT_TRYC(cudaMalloc((void**)&planes, nfilt * sizeof(float2)));
+    LCT_TRYC(cudaMemset(planes, 0, nfilt * sizeof(float2)));
+    LCT_TRYC(cudaMalloc((void**)&dz, sizeof(int) * d->psf_count));
+    LCT_TRYC(cudaMalloc((void**)&dyx, sizeof(int) * d->psf_count));
+    LCT_TRYC(cudaMemcpy(dz, d->psf_z, sizeof(int) * d->psf_count, cudaMemcpyHostToDevice));
+    LCT_TRYC(cudaMemcpy(dyx, d->psf_yx, sizeof(int) * d->psf_count, cudaMemcpyHostToDevice));
+    lct::psf_planes_kernel<<<dim3((d->psf_count + 255) / 256, M + 1), 256>>>(planes, dz, dyx, d->psf_count, d->psf_value, M, L);
+    {
+        auto kern = lct::column_fft_kernel<PH, CT>;
+        constexpr size_t smem = (size_t)L * CT * sizeof(float2);
+        if (smem > 48 * 1024) LCT_TRYC(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<dim3(L / CT, M + 1), PH::TL * CT, smem>>>(planes);
+    }
+    {
+        auto kern = lct::row_fft_wiener_kernel<PL, PH, RB>;
+        constexpr int RS = L + PL::R0 + ((PL::TL < 16) ? 8 : 0);
+        constexpr size_t smem = (size_t)RB * RS * sizeof(float2);
+        if (smem > 48 * 1024) LCT_TRYC(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lct::FilterBuildParams fp{M, N, planes, out, fused ? 1 : 0, 1.0f / d->snr, scale, d->method_bp};
+        kern<<<dim3(L / RB, M + 1), PL::TL * RB, smem>>>(fp);
+    }
+    LCT_TRYC(cudaGetLastError());
+    LCT_TRYC(cudaDeviceSynchronize());
+#undef LCT_TRYC
+    cleanup();
+    return LCT_OK;
+}
+
 struct DeviceBand {
     float4* ell = nullptr;
     int* rowptr = nullptr;
@@ -194,7 +235,10 @@ void lct_plan_destroy(lct_plan* plan) {
 int lct_plan_create(const lct_desc* d, lct_plan** out) {
     if (!d || !out) return fail(LCT_ERR_INVALID, "null descriptor");
     *out = nullptr;
-    if (!d->mtx_rowptr || !d->mtx_colidx || !d->mtx_vals || !d->filter_half) return fail(LCT_ERR_INVALID, "null operator table");
+    if (!d->mtx_rowptr || !d->mtx_colidx || !d->mtx_vals) return fail(LCT_ERR_INVALID, "null operator table");
+    const bool device_filter = d->filter_half == nullptr;
+    if (device_filter && (!d->psf_z || !d->psf_yx || d->psf_count <= 0 || !(d->snr > 0.f) || !(d->psf_value > 0.f)))
+        return fail(LCT_ERR_INVALID, "neither a filter nor a PSF support was given");
     const int M = d->time_bins, N = d->spatial;
     if (!lct::supported_M(M) || !lct::supported_N(N)) return fail(LCT_ERR_UNSUPPORTED, "size not compiled");
     if (d->device < 0 || d->device >= kMaxDevices) return fail(LCT_ERR_INVALID, "bad device ordinal");
@@ -217,28 +261,43 @@ int lct_plan_create(const lct_desc* d, lct_plan** out) {
     LCT_TRY(upload_band(ht.mtx_ell, ht.mtx_rowptr, ht.mtx_vals, p->mtx));
     LCT_TRY(upload_band(ht.mtxi_ell, ht.mtxi_rowptr, ht.mtxi_vals, p->mtxi));
     LCT_TRY(upload_band(ht.mtxi_ell_falloff, ht.mtxi_rowptr, ht.mtxi_vals_falloff, p->mtxi_falloff));
-    float2* dev_filt = nullptr;
-    if (lct::plane_fusable(N) && !(d->reserved & LCT_FLAG_NO_PLANE_FUSION)) {
-        // fused layout: [kt][kw/2][plane row][kw&1] -- both output parities of a row in one 128-bit load,
-        // rows in the order the forward H stages leave them
-        const int L = 2 * N;
-        const float2* nat = reinterpret_cast<const float2*>(d->filter_half);
-        std::vector<float2> perm(nfilt);
-        std::vector<int> kh_of_row(L);
-        for (int r = 0; r < L; ++r) {
-            int rc = -1;
-            LCT_SWITCH_N(N, (lct::plane_row_freq<kN>(r)));
-            kh_of_row[r] = rc;
-        }
-        for (int kt = 0; kt <= M; ++kt)
-            for (int kw = 0; kw < L; ++kw)
-                for (int r = 0; r < L; ++r)
-                    perm[(((size_t)kt * N + (kw >> 1)) * L + r) * 2 + (kw & 1)] = nat[((size_t)kt * L + kh_of_row[r]) * L + kw];
-        LCT_TRY(to_device(perm.data(), nfilt, &p->filt_plane));
-        dev_filt = p->filt_plane;
+    // fold torch.ifft's 1/(2M*2N*2N) (tflct.py:151) into the filter; a power of two, so exact
+    const float scale = 1.0f / (8.0f * (float)M * (float)N * (float)N);
+    const bool fused = lct::plane_fusable(N) && !(d->reserved & LCT_FLAG_NO_PLANE_FUSION);
+    float2** slot = fused ? &p->filt_plane : &p->filt;
+    if (device_filter) {
+        cudaError_t e = cudaMalloc((void**)slot, nfilt * sizeof(float2));
+        if (e != cudaSuccess) { lct_plan_destroy(p); return fail(LCT_ERR_NOMEM, "filter allocation", e); }
+        for (int i = 0; i < d->psf_count; ++i)
+            if (d->psf_z[i] < 0 || d->psf_z[i] >= 2 * M || d->psf_yx[i] < 0 || d->psf_yx[i] >= 4 * N * N) {
+                lct_plan_destroy(p);
+                return fail(LCT_ERR_INVALID, "PSF voxel out of range");
+            }
+        rc = -1;
+        LCT_SWITCH_N(N, (build_filter_on_device<kN>(d, *slot, fused, scale)));
+        if (rc) { lct_plan_destroy(p); return rc < 0 ? fail(LCT_ERR_UNSUPPORTED, "size not compiled") : rc; }
     } else {
-        LCT_TRY(to_device(reinterpret_cast<const float2*>(d->filter_half), nfilt, &p->filt));
-        dev_filt = p->filt;
+        if (fused) {
+            // fused layout: [kt][kw/2][plane row][kw&1] -- both output parities of a row in one 128-bit load,
+            // rows in the order the forward H stages leave them
+            const int L = 2 * N;
+            const float2* nat = reinterpret_cast<const float2*>(d->filter_half);
+            std::vector<float2> perm(nfilt);
+            std::vector<int> kh_of_row(L);
+            for (int r = 0; r < L; ++r) {
+                int rc = -1;
+                LCT_SWITCH_N(N, (lct::plane_row_freq<kN>(r)));
+                kh_of_row[r] = rc;
+            }
+            for (int kt = 0; kt <= M; ++kt)
+                for (int kw = 0; kw < L; ++kw)
+                    for (int r = 0; r < L; ++r)
+                        perm[(((size_t)kt * N + (kw >> 1)) * L + r) * 2 + (kw & 1)] = nat[((size_t)kt * L + kh_of_row[r]) * L + kw];
+            LCT_TRY(to_device(perm.data(), nfilt, slot));
+        } else {
+            LCT_TRY(to_device(reinterpret_cast<const float2*>(d->filter_half), nfilt, slot));
+        }
+        scale_filter_kernel<<<1024, 256>>>(*slot, nfilt, scale);
     }
 #undef LCT_TRY
     {
@@ -257,8 +316,6 @@ int lct_plan_create(const lct_desc* d, lct_plan** out) {
             return fail(LCT_ERR_CUDA, "fork event creation");
         }
     }
-    // fold torch.ifft's 1/(2M*2N*2N) (tflct.py:151) into the filter; a power of two, so exact
-    scale_filter_kernel<<<1024, 256>>>(dev_filt, nfilt, 1.0f / (8.0f * (float)M * (float)N * (float)N));
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { lct_plan_destroy(p); return fail(LCT_ERR_CUDA, "filter scaling", e); }
     *out = p;

@@ -2,6 +2,8 @@
 (``tflct.lct`` and ``feature_propagation.LCT``)."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -49,13 +51,25 @@ class LctLayerBase(nn.Module):
         # host operators in the compact forms the kernels consume (tflct.py:49-70)
         self._csr = ops.resampling_csr(self._M)
         self._falloff = ops.falloff(self._M, material)
-        self._filter_half = ops.inverse_filter_half(self._N, self._M, self.width / self.trange, method, self.snr)
+        # the inverse filter (tflct.py:55-65): only the PSF support is found on the host; the library
+        # builds the spectrum on the GPU in todev().  HIDDENPOSE_LCT_HOST_FILTER=1 builds it on the host instead.
+        self._psf = ops.psf_support(self._N, self._M, self.width / self.trange)
+        self._filter_half_cache = None
+        self._host_filter = os.environ.get("HIDDENPOSE_LCT_HOST_FILTER", "0") not in ("", "0")
         self._lapw = ops.laplacian_filter() if method == "bp" else None       # tflct.py:73-77
         self._plan, self._dev, self.dnum = None, torch.device("cpu"), 2
         # reduce the volume's per-channel min/max in the last kernel and leave them on the output for
         # normalize_feature (FeaturePropagation turns this on: NlosPose.py:53-54 always normalises next)
         self.fuse_minmax = False
         self._dense_cache = {}
+
+    @property
+    def _filter_half(self):
+        """Host-built half spectrum (M+1, 2N, 2N) complex64; only materialised when asked for."""
+        if self._filter_half_cache is None:
+            self._filter_half_cache = ops.inverse_filter_half(self._N, self._M, self.width / self.trange,
+                                                              self._method, self.snr)
+        return self._filter_half_cache
 
     # -- reference attributes, materialised on demand --------------------------------
     @property
@@ -121,7 +135,9 @@ class LctLayerBase(nn.Module):
         self._dev, self.dnum = d, int(dnum)
         if d.type == "cuda":
             if self._plan is None or self._plan.device != d:
-                self._plan = LctPlan(self._M, self._N, self._csr, self._falloff, self._filter_half, d, lapw=self._lapw)
+                self._plan = LctPlan(self._M, self._N, self._csr, self._falloff,
+                                     self._filter_half if self._host_filter else None, d, lapw=self._lapw,
+                                     psf=self._psf, snr=self.snr, method_bp=(self._method == "bp"))
         else:
             self._plan = None
         return self

@@ -22,7 +22,8 @@ def _i32_array(values):
 class LctPlan:
     """Owns one ``lct_plan*`` (immutable device constants) on one CUDA device."""
 
-    def __init__(self, M, N, csr, falloff, filter_half, device, lapw=None, workspace_limit_bytes=16 << 30, flags=0):
+    def __init__(self, M, N, csr, falloff, filter_half, device, lapw=None, workspace_limit_bytes=16 << 30, flags=0,
+                 psf=None, snr=0.1, method_bp=False):
         if device.type != "cuda":
             raise RuntimeError("LctPlan needs a CUDA device; there is no CPU implementation of this layer")
         self.lib = _native.load()
@@ -32,19 +33,32 @@ class LctPlan:
         rowptr = np.ascontiguousarray(csr[0], dtype=np.int32)
         colidx = np.ascontiguousarray(csr[1], dtype=np.int32)
         vals = np.ascontiguousarray(csr[2], dtype=np.float32)
-        filt = np.ascontiguousarray(filter_half, dtype=np.complex64)
-        if filt.shape != (M + 1, 2 * N, 2 * N):
-            raise ValueError(f"filter_half must be {(M + 1, 2 * N, 2 * N)}, got {filt.shape}")
+        # either the host-built half spectrum, or the PSF support from which the library builds it on the GPU
+        filt = psf_z = psf_yx = None
+        if filter_half is not None:
+            filt = np.ascontiguousarray(filter_half, dtype=np.complex64)
+            if filt.shape != (M + 1, 2 * N, 2 * N):
+                raise ValueError(f"filter_half must be {(M + 1, 2 * N, 2 * N)}, got {filt.shape}")
+        elif psf is not None:
+            z, y, x, val = psf
+            psf_z = np.ascontiguousarray(z, dtype=np.int32)
+            psf_yx = np.ascontiguousarray(np.asarray(y, dtype=np.int64) * (2 * N) + np.asarray(x, dtype=np.int64), dtype=np.int32)
+        else:
+            raise ValueError("LctPlan needs filter_half or psf")
         fall = None if falloff is None else np.ascontiguousarray(falloff, dtype=np.float32)
         f32p, i32p = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
         desc = _native.LctDesc(
             time_bins=M, spatial=N, device=device.index if device.index is not None else torch.cuda.current_device(),
             reserved=int(flags), mtx_rowptr=rowptr.ctypes.data_as(i32p), mtx_colidx=colidx.ctypes.data_as(i32p),
             mtx_vals=vals.ctypes.data_as(f32p), falloff=None if fall is None else fall.ctypes.data_as(f32p),
-            filter_half=filt.view(np.float32).ctypes.data_as(f32p))
+            filter_half=None if filt is None else filt.view(np.float32).ctypes.data_as(f32p),
+            psf_z=None if psf_z is None else psf_z.ctypes.data_as(i32p),
+            psf_yx=None if psf_yx is None else psf_yx.ctypes.data_as(i32p),
+            psf_count=0 if psf_z is None else len(psf_z), psf_value=0.0 if psf is None else float(psf[3]),
+            snr=float(snr), method_bp=1 if method_bp else 0)
         handle = ctypes.c_void_p()
         _native.check(self.lib.lct_plan_create(ctypes.byref(desc), ctypes.byref(handle)))
-        del rowptr, colidx, vals, fall, filt      # host tables were copied to the device
+        del rowptr, colidx, vals, fall, filt, psf_z, psf_yx      # host tables were copied to the device
         self.handle = handle
 
     def __del__(self):

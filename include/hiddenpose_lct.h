@@ -42,7 +42,7 @@ extern "C" {
 #define LCT_ERR_WORKSPACE 4    /* workspace smaller than lct_plan_workspace_bytes(plan, 1) */
 #define LCT_ERR_NOMEM 5
 
-#define LCT_ABI_VERSION 1
+#define LCT_ABI_VERSION 2
 
 /* lct_desc.flags */
 #define LCT_FLAG_NO_PLANE_FUSION 1   /* keep K2/K3/K4 as three kernels even when the plane fits on chip */
@@ -60,7 +60,16 @@ typedef struct lct_desc {
     const float* mtx_vals;      /* nnz                                                            */
     const float* falloff;       /* M     gridz**4 | **2 (tflct.py:123-127); NULL = no falloff     */
     const float* filter_half;   /* (M+1, 2N, 2N, 2) interleaved re/im: planes kt = 0..M of invpsf
-                                   (tflct.py:57-65), unscaled                                     */
+                                   (tflct.py:57-65), unscaled; or NULL to have the library build the
+                                   filter on the device from the PSF support below                */
+    /* PSF support (utils/helper.py:72-125): the non-zero voxels of definePsf's (2M, 2N, 2N) volume,
+       after its roll/transpose.  Only read when filter_half is NULL.                              */
+    const int32_t* psf_z;       /* psf_count  time index of each voxel, in [0, 2M)                */
+    const int32_t* psf_yx;      /* psf_count  y * 2N + x of each voxel                            */
+    int32_t psf_count;
+    float psf_value;            /* common voxel value 1/sqrt(count) (helper.py:112)               */
+    float snr;                  /* tflct.py:42                                                    */
+    int32_t method_bp;          /* 0: 'lct' Wiener inverse (tflct.py:60); 1: 'bp' conj(fpsf) (:62) */
 } lct_desc;
 
 int lct_abi_version(void);

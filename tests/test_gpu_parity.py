@@ -26,7 +26,7 @@ def _layer(N, M, bin_len, D, method="lct", material="diffuse"):
 def test_native_library_is_loaded():
     from hiddenpose_b200 import _native
     lib = _native.load()
-    assert lib.lct_abi_version() == 1
+    assert lib.lct_abi_version() == 2
     with open("/proc/self/maps") as f:
         assert "libhiddenpose_lct.so" in f.read()
 
@@ -289,3 +289,18 @@ def test_cuda_graph_capture_replays_the_layer():
             graph.replay()
             torch.cuda.synchronize()
             assert torch.equal(static_y, layer(fresh, [0] * B, [M] * B))
+
+
+@pytest.mark.parametrize("M,N,method", [(64, 16, "lct"), (128, 64, "lct"), (64, 128, "lct"), (64, 32, "bp")])
+def test_device_built_filter_matches_host_built(M, N, method, monkeypatch):
+    """Row f3: the filter built on the GPU from the PSF support gives the same volumes as the one built on
+    the host with NumPy in double precision (both fused and five-kernel layouts)."""
+    import hiddenpose_b200 as hp
+    x = torch.rand(2, 1, M, N, N, device="cuda")
+    outs = []
+    for host in ("0", "1"):
+        monkeypatch.setenv("HIDDENPOSE_LCT_HOST_FILTER", host)
+        layer = hp.lct(spatial=N, crop=M, bin_len=0.01 * 512 / M, method=method)
+        layer.todev("cuda:0", 1)
+        outs.append(layer(x, [0, 0], [M, M]))
+    assert O.rel_l2(outs[0].cpu(), outs[1].cpu()) <= 2e-6
