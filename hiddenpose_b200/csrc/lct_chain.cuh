@@ -23,7 +23,7 @@ template <int M> struct TimeInvPlan { using type = typename ColPlan<M>::type; };
 template <> struct TimeFwdPlan<512> { using type = Plan<16, 16, 2>; };   // 410 us vs 447 us with (16,32)
 template <int L> struct RowFwdPlan { using type = typename ColPlan<L>::type; };
 template <int L> struct RowInvPlan { using type = typename ColPlan<L>::type; };
-template <> struct RowFwdPlan<512> { using type = Plan<8, 8, 8>; };        // cfg5: 373 us vs 412 us with (16,32)
+template <> struct RowFwdPlan<512> { using type = Plan<32, 16>; };         // cfg5: 248 us; (8,8,8) 385 us, (16,32) 412 us
 
 // Line plans for K3 (lanes run along the contiguous line): two stages only.
 template <int L> struct LinePlan;
@@ -32,7 +32,7 @@ template <> struct LinePlan<32>  { using type = Plan<8, 4>; };
 template <> struct LinePlan<64>  { using type = Plan<8, 8>; };
 template <> struct LinePlan<128> { using type = Plan<16, 8>; };
 template <> struct LinePlan<256> { using type = Plan<16, 16>; };
-template <> struct LinePlan<512> { using type = Plan<32, 16>; };
+template <> struct LinePlan<512> { using type = Plan<32, 16>; };        // (16,32) measured the same
 
 // column tile (in columns of the flattened H*W axis) for the T-axis kernels
 template <int M> struct TimeTile { static constexpr int CT = (M >= 512) ? 16 : 32; };     // 16-wide tiles measured slower below M = 512
