@@ -20,7 +20,10 @@ template <> struct ColPlan<512> { using type = Plan<16, 32>; };    // measured o
 // The two time kernels may prefer different factorizations of the same length.
 template <int M> struct TimeFwdPlan { using type = typename ColPlan<M>::type; };
 template <int M> struct TimeInvPlan { using type = typename ColPlan<M>::type; };
-template <> struct TimeFwdPlan<512> { using type = Plan<16, 16, 2>; };   // 410 us vs 447 us with (16,32)
+// cfg3, one 512-thread block of 32 columns per SM: K1 395 us, K5 337 us; (16,16,2) / (16,32) on
+// 16-column tiles at two blocks per SM: 419 / 358 us
+template <> struct TimeFwdPlan<512> { using type = Plan<32, 16>; };
+template <> struct TimeInvPlan<512> { using type = Plan<32, 16>; };
 template <int L> struct RowFwdPlan { using type = typename ColPlan<L>::type; };
 template <int L> struct RowInvPlan { using type = typename ColPlan<L>::type; };
 template <> struct RowFwdPlan<512> { using type = Plan<32, 16>; };         // cfg5: 248 us; (8,8,8) 385 us, (16,32) 412 us
@@ -35,7 +38,7 @@ template <> struct LinePlan<256> { using type = Plan<16, 16>; };
 template <> struct LinePlan<512> { using type = Plan<32, 16>; };        // (16,32) measured the same
 
 // column tile (in columns of the flattened H*W axis) for the T-axis kernels
-template <int M> struct TimeTile { static constexpr int CT = (M >= 512) ? 16 : 32; };     // 16-wide tiles measured slower below M = 512
+template <int M> struct TimeTile { static constexpr int CT = 32; };     // 16-wide tiles measured slower at every M
 // column tile along W for the H-axis kernels
 template <int N> struct RowTile { static constexpr int CT = (N >= 256) ? 16 : (N < 32 ? N : 32); };
 // rows per block for K3
