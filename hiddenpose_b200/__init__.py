@@ -6,6 +6,7 @@ Hagtaril/HiddenPose): :class:`tflct.lct`, :class:`feature_propagation.LCT`,
 hand-written CUDA library behind ``include/hiddenpose_lct.h``.
 """
 from ._native import build_native, load as load_native          # noqa: F401
+from .feature_extraction import FeatureExtraction, skip_sum      # noqa: F401
 from .feature_propagation import LCT, FeaturePropagation, VisibleNet, normalize, normalize_feature   # noqa: F401
 from .lct_function import LctFunction, LctPlan                   # noqa: F401
 from .streaming import LctStreamer                               # noqa: F401

@@ -28,6 +28,7 @@ SYMBOLS = (
     "lct_plan_time_bins", "lct_plan_spatial", "lct_plan_workspace_bytes", "lct_forward", "lct_backward",
     "lct_bp_laplacian", "lct_forward_host", "lct_run_staged", "lct_forward_minmax", "lct_minmax",
     "lct_normalize_feature", "lct_normalize_feature_backward",
+    "lct_skip_workspace_bytes", "lct_skip_sum", "lct_skip_sum_backward",
 )
 
 
@@ -111,6 +112,12 @@ def load():
     lib.lct_normalize_feature_backward.argtypes = [vp, vp, vp, vp, vp, i32, ctypes.c_int64, ctypes.c_float, vp]
     lib.lct_bp_laplacian.restype = ctypes.c_int
     lib.lct_bp_laplacian.argtypes = [vp, vp, vp, i32, ctypes.POINTER(ctypes.c_float), i32, vp]
+    lib.lct_skip_workspace_bytes.restype = sz
+    lib.lct_skip_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.lct_skip_sum.restype = ctypes.c_int
+    lib.lct_skip_sum.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.lct_skip_sum_backward.restype = ctypes.c_int
+    lib.lct_skip_sum_backward.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, sz, vp]
     lib.lct_forward_host.restype = ctypes.c_int
     lib.lct_forward_host.argtypes = [vp, vp, pi32, pi32, i32, i32, i32, vp, vp]
     _lib = lib

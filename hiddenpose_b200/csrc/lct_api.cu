@@ -15,6 +15,7 @@
 #include "lct_chain.cuh"
 #include "lct_filter_build.cuh"
 #include "lct_normalize.cuh"
+#include "lct_skipconv.cuh"
 #include "lct_stencil.cuh"
 #include "lct_tables.h"
 
@@ -481,6 +482,92 @@ int lct_bp_laplacian(const lct_plan* plan, const float* vol, float* out, int32_t
     else
         lct::laplacian_kernel<<<blocks, threads, 0, (cudaStream_t)stream_>>>(vol, out, channels, plan->M, plan->N, w);
     LCT_CUDA(cudaGetLastError());
+    return LCT_OK;
+}
+
+static bool skip_args_ok(int32_t B, int32_t D, int32_t T, int32_t N) {
+    return B > 0 && B <= 65535 && D > 0 && T > 0 && N >= 4 && (N % 4) == 0;
+}
+
+extern "C++" {
+// launch shape of one skip-branch pass on the current device (the SM count is looked up once per device)
+struct SkipLaunch { bool ring; int chunk; dim3 grid; size_t smem; };
+
+static SkipLaunch skip_launch(int32_t B, int32_t T, int32_t N, bool single_channel_window) {
+    static int sms[64] = {0};
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+        if (sms[dev] == 0 && (cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms[dev] <= 0))
+            sms[dev] = 148;
+        n = sms[dev];
+    }
+    SkipLaunch l;
+    l.ring = single_channel_window && lct::skip_ring_ok(N);
+    l.chunk = lct::skip_chunk(B, T, N, n, l.ring);
+    l.grid = l.ring ? lct::skip_ring_grid(B, T, N, l.chunk) : lct::skip_grid(B, T, N, l.chunk);
+    l.smem = l.ring ? lct::skip_ring_smem(N) : 0;
+    return l;
+}
+
+template <int MODE> static cudaError_t skip_run(const SkipLaunch& l, const lct::SkipParams& p, cudaStream_t stream) {
+    if (l.ring) {
+        static std::mutex mu;
+        static bool ready[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            if (dev >= 0 && dev < 64 && !ready[dev]) {
+                cudaError_t e = cudaFuncSetAttribute(lct::skip_ring_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+                if (e != cudaSuccess) return e;
+                ready[dev] = true;
+            }
+        }
+        lct::skip_ring_kernel<MODE><<<l.grid, lct::kSkipThreads, l.smem, stream>>>(p);
+    } else {
+        lct::skip_kernel<MODE><<<l.grid, lct::kSkipThreads, 0, stream>>>(p);
+    }
+    return cudaGetLastError();
+}
+}  // extern "C++"
+
+size_t lct_skip_workspace_bytes(int32_t B, int32_t T, int32_t N) {
+    if (!skip_args_ok(B, 1, T, N)) return 0;
+    const SkipLaunch l = skip_launch(B, T, N, true);
+    return (size_t)l.grid.x * l.grid.y * l.grid.z * 27 * sizeof(float);
+}
+
+int lct_skip_sum(const float* feat, const float* x, const float* w, int32_t B, int32_t D, int32_t T, int32_t N,
+                 float* out, void* stream_) {
+    if (!feat || !x || !w || !out || !skip_args_ok(B, D, T, N)) return fail(LCT_ERR_INVALID, "bad argument");
+    if (((uintptr_t)feat | (uintptr_t)x | (uintptr_t)out) & 15) return fail(LCT_ERR_INVALID, "buffers must be 16-byte aligned");
+    if (x == out) return fail(LCT_ERR_INVALID, "x must not alias out");
+    const SkipLaunch l = skip_launch(B, T, N, true);
+    lct::SkipParams p{x, feat, out, w, D, T, N, l.chunk};
+    LCT_CUDA(skip_run<lct::kSkipForward>(l, p, (cudaStream_t)stream_));
+    return LCT_OK;
+}
+
+int lct_skip_sum_backward(const float* g, const float* x, const float* w, int32_t B, int32_t D, int32_t T, int32_t N,
+                          float* gx, float* gw, void* ws, size_t ws_bytes, void* stream_) {
+    if (!g || !skip_args_ok(B, D, T, N) || (!gx && !gw)) return fail(LCT_ERR_INVALID, "bad argument");
+    if (((uintptr_t)g | (uintptr_t)x | (uintptr_t)gx) & 15) return fail(LCT_ERR_INVALID, "buffers must be 16-byte aligned");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (gx) {
+        if (!w || gx == g) return fail(LCT_ERR_INVALID, "bad argument");
+        const SkipLaunch l = skip_launch(B, T, N, D == 1);          // the window is sum_d g[b, d]: staged copies need D == 1
+        lct::SkipParams p{g, nullptr, gx, w, D, T, N, l.chunk};
+        LCT_CUDA(skip_run<lct::kSkipDataGrad>(l, p, stream));
+    }
+    if (gw) {
+        const SkipLaunch l = skip_launch(B, T, N, true);
+        const size_t blocks = (size_t)l.grid.x * l.grid.y * l.grid.z;
+        if (!x || !ws || ws_bytes < blocks * 27 * sizeof(float)) return fail(LCT_ERR_WORKSPACE, "workspace too small");
+        lct::SkipParams p{x, g, static_cast<float*>(ws), nullptr, D, T, N, l.chunk};
+        LCT_CUDA(skip_run<lct::kSkipWeightGrad>(l, p, stream));
+        lct::skip_weight_reduce_kernel<<<1, 27 * 32, 0, stream>>>(static_cast<const float*>(ws), (int)blocks, gw);
+        LCT_CUDA(cudaGetLastError());
+    }
     return LCT_OK;
 }
 

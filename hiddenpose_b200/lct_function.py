@@ -204,3 +204,44 @@ class NormalizeFeatureFunction(torch.autograd.Function):
             _native.check(lib.lct_normalize_feature_backward(x.data_ptr(), gout.data_ptr(), keys.data_ptr(), gx.data_ptr(),
                                                              sums.data_ptr(), b * c, elems, ctx.scale, stream))
         return gx, None, None
+
+
+class SkipSumFunction(torch.autograd.Function):
+    """``feat + F.conv3d(x, weights, stride=1, padding=1)`` (feature_extraction.py:166-171) on the CUDA library.
+
+    ``feat`` (B, D, T, N, N), ``x`` (B, 1, T, N, N), ``weights`` (1, 1, 3, 3, 3), all CUDA float32.
+    Backward: d/d feat is the incoming gradient itself; d/d x and d/d weights are one stencil pass each.
+    """
+
+    @staticmethod
+    def forward(ctx, feat, x, weights):
+        lib = _native.load()
+        feat, x, w = feat.contiguous(), x.contiguous(), weights.detach().contiguous()
+        B, D, T, N = feat.shape[0], feat.shape[1], feat.shape[2], feat.shape[3]
+        out = torch.empty_like(feat)
+        with torch.cuda.device(feat.device):
+            stream = torch.cuda.current_stream(feat.device).cuda_stream
+            _native.check(lib.lct_skip_sum(feat.data_ptr(), x.data_ptr(), w.data_ptr(), B, D, T, N, out.data_ptr(), stream))
+        ctx.save_for_backward(x, w)
+        ctx.dims = (B, D, T, N)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        lib = _native.load()
+        B, D, T, N = ctx.dims
+        g = g.contiguous().float()
+        need_x, need_w = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        gx = torch.empty_like(x) if need_x else None
+        gw = torch.empty(27, dtype=torch.float32, device=x.device) if need_w else None
+        if need_x or need_w:
+            with torch.cuda.device(x.device):
+                nbytes = lib.lct_skip_workspace_bytes(B, T, N) if need_w else 0
+                ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
+                stream = torch.cuda.current_stream(x.device).cuda_stream
+                _native.check(lib.lct_skip_sum_backward(
+                    g.data_ptr(), x.data_ptr(), w.data_ptr(), B, D, T, N,
+                    gx.data_ptr() if need_x else None, gw.data_ptr() if need_w else None,
+                    ws.data_ptr(), nbytes, stream))
+        return (g if ctx.needs_input_grad[0] else None), gx, (gw.view(1, 1, 3, 3, 3) if need_w else None)

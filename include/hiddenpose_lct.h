@@ -16,6 +16,9 @@
  *   lct_bp_laplacian   <- the method=='bp' tail             models/tflct.py:164-175
  *   lct_normalize_feature[_backward], lct_minmax, lct_forward_minmax
  *                      <- normalize_feature                 models/feature_propagation.py:273-286
+ *   lct_skip_sum[_backward]
+ *                      <- FeatureExtraction's skip branch   models/feature_extraction.py:141-145,166-171
+ *                         (the op that produces the LCT's input, NlosPose.py:51-53)
  *
  * Plain C types only: pointers, sizes, integer return codes (0 = success).  Nothing
  * throws across this boundary.  Device pointers are raw CUDA device addresses; `stream`
@@ -42,7 +45,7 @@ extern "C" {
 #define LCT_ERR_WORKSPACE 4    /* workspace smaller than lct_plan_workspace_bytes(plan, 1) */
 #define LCT_ERR_NOMEM 5
 
-#define LCT_ABI_VERSION 2
+#define LCT_ABI_VERSION 3
 
 /* lct_desc.flags */
 #define LCT_FLAG_NO_PLANE_FUSION 1   /* keep K2/K3/K4 as three kernels even when the plane fits on chip */
@@ -142,6 +145,27 @@ int lct_run_staged(const lct_plan* plan, const float* in, const int32_t* tbe, co
  */
 int lct_bp_laplacian(const lct_plan* plan, const float* vol, float* out, int32_t channels,
                      const float* lapw, int32_t adjoint, void* stream);
+
+/*
+ * Skip branch of FeatureExtraction (feature_extraction.py:166-171), the op that feeds the LCT:
+ *     out[b, d] = feat[b, d] + conv3d(x[b], w, stride 1, padding 1)         (zero padding,
+ *     cross-correlation as F.conv3d; the one-channel result is broadcast over feat's D channels)
+ *   feat, out  device, float32, (B, D, T, N, N); out may be feat (in place)
+ *   x          device, float32, (B, 1, T, N, N); must not alias out
+ *   w          DEVICE, 27 floats, the learnable (1,1,3,3,3) parameter in (t, y, x) order
+ * N must be a multiple of 4 and the pointers 16-byte aligned.  Runs on the current device.
+ *
+ * lct_skip_sum_backward: given g = d loss / d out (B, D, T, N, N),
+ *     gx[b]  = conv3d^T(sum_d g[b, d], w)            (B, 1, T, N, N), skipped when gx == NULL
+ *     gw[k]  = sum_{b,d,p} g[b,d,p] * x[b, p + k - 1]  27 floats,     skipped when gw == NULL
+ * (d loss / d feat is g itself).  gw needs lct_skip_workspace_bytes(B, T, N) bytes of device scratch;
+ * the reduction order is fixed, so results are reproducible run to run.
+ */
+size_t lct_skip_workspace_bytes(int32_t B, int32_t T, int32_t N);
+int lct_skip_sum(const float* feat, const float* x, const float* w, int32_t B, int32_t D, int32_t T, int32_t N,
+                 float* out, void* stream);
+int lct_skip_sum_backward(const float* g, const float* x, const float* w, int32_t B, int32_t D, int32_t T, int32_t N,
+                          float* gx, float* gw, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Host-buffer convenience: copies x from host memory, runs lct_forward, copies y back and

@@ -26,7 +26,7 @@ def _layer(N, M, bin_len, D, method="lct", material="diffuse"):
 def test_native_library_is_loaded():
     from hiddenpose_b200 import _native
     lib = _native.load()
-    assert lib.lct_abi_version() == 2
+    assert lib.lct_abi_version() == 3
     with open("/proc/self/maps") as f:
         assert "libhiddenpose_lct.so" in f.read()
 

@@ -111,7 +111,7 @@ def test_shared_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), sym
     lib.lct_abi_version.restype = ctypes.c_int
-    assert lib.lct_abi_version() == 2
+    assert lib.lct_abi_version() == 3
     lib.lct_error_string.restype = ctypes.c_char_p
     assert lib.lct_error_string(2).startswith(b"unsupported")
 
