@@ -264,6 +264,27 @@ def main():
     barrier()
     fb_ms = sharding.max_over_ranks(sum(a.elapsed_time(b) for a, b in fb_events), dev)
 
+    # ---- the two ops either side of the layer in the model, device-resident -----
+    from hiddenpose_b200.feature_extraction import skip_sum
+    from hiddenpose_b200.feature_propagation import normalize_feature
+    KN = min(K, 50)
+    w27 = torch.randn(1, 1, 3, 3, 3, device=dev)
+    feat = torch.randn_like(x)
+    side_ms = {}
+    with torch.no_grad():
+        for name, fn in (("skip_sum", lambda: skip_sum(feat, x, w27)), ("normalize_feature", lambda: normalize_feature(y))):
+            for _ in range(3):
+                fn()
+            evs = [new_events(2) for _ in range(KN)]
+            for a, b in evs:
+                flush.zero_()
+                a.record()
+                fn()
+                b.record()
+            torch.cuda.synchronize()
+            side_ms[name] = statistics.median(a.elapsed_time(b) for a, b in evs)
+    del feat
+
     # ---- end to end: pinned host input -> H2D -> forward -> D2H of the volume, every step ---
     # through the public streaming API (hiddenpose_b200.LctStreamer): consecutive steps overlap
     # their upload / transform / download legs; every step still moves its own input and output.
@@ -345,6 +366,13 @@ def main():
                          "note": "per-kernel times from lct_run_staged (single stream); the headline runs two "
                                  "channel groups on two streams so consecutive kernels overlap"},
             "stages": stages,
+            "neighbours": {
+                "skip_sum": {"what": "x_conv1 + conv3d(x, w 3x3x3) -- FeatureExtraction's skip branch, writes the layer's input",
+                             "ms": side_ms["skip_sum"], "bytes": 12 * M * N * N * C,
+                             "gbs": 12 * M * N * N * C / (side_ms["skip_sum"] * 1e-3) / 1e9},
+                "normalize_feature": {"what": "per-channel min/max + affine on the layer's output (min/max not fused here)",
+                                      "ms": side_ms["normalize_feature"], "bytes": 12 * M * N * N * C,
+                                      "gbs": 12 * M * N * N * C / (side_ms["normalize_feature"] * 1e-3) / 1e9}},
         }
         if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only
             times = cpu_oracle_rate(M, N, args.cpu_reps, 2)
