@@ -250,7 +250,7 @@ int lct_plan_create(const lct_desc* d, lct_plan** out) {
 
     // validate the operator and derive the banded row tables for mtx and mtxi = mtx^T (helper.py:61)
     lct::HostTables ht;
-    const std::string why = lct::build_tables(M, d->mtx_rowptr, d->mtx_colidx, d->mtx_vals, d->falloff, ht);
+    const std::string why = lct::build_tables(M, d->mtx_rowptr, d->mtx_colidx, d->mtx_vals, d->falloff, lct::time_tail_rows(M), ht);
     if (!why.empty()) return fail(LCT_ERR_INVALID, why.c_str());
 
     lct_plan* p = new (std::nothrow) lct_plan();

@@ -104,6 +104,15 @@ template <int N, class Launcher> int launch_plane(const Params& p, Launcher& l) 
         default: rc = -1;                                       \
     }
 
+// Rows of mtx below this index may carry more than three entries: the time-forward kernel looks for a
+// CSR tail only at the first input of each stage-0 butterfly (positions < st(0), i.e. rows < 2 st(0)).
+template <int M> constexpr int time_tail_rows_for() { return 2 * TimeFwdPlan<M>::type::st(0); }
+inline int time_tail_rows(int M) {
+    int rc = 0;
+    LCT_SWITCH_M(M, (time_tail_rows_for<kM>()));
+    return rc < 0 ? 0 : rc;
+}
+
 // Resampling-operator tables the chain needs (device pointers on the GPU; see lct_tables.h).
 struct BandTable { const float4* ell; const int* rowptr; const float* vals; };
 struct ChainTables {

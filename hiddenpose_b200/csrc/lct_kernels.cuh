@@ -28,6 +28,7 @@
 #include <type_traits>
 
 #include "lct_fft.cuh"
+#include "lct_tables.h"
 
 namespace lct {
 
@@ -170,7 +171,7 @@ struct Params {
     const float2* filt;         // (M+1, 2N, 2N), already scaled by 1/(8 M N N)
     int conj_filter;
     // Resampling operator used by this launch (mtx rows for K1, mtxi rows for K5): one 16-byte
-    // record per row {start | len << 16, w0, w1, w2} (lct_tables.h); rows longer than 3
+    // record per row {start * kEllStride, w0, w1, w2} (lct_tables.h); rows longer than 3
     // continue in vals[rowptr[row] + 3 ...].
     const float4* ell;
     const int* rowptr;
@@ -205,18 +206,23 @@ LCT_DEV void minmax_commit(unsigned long long* keys, int c, unsigned long long k
 }
 
 
-// sum_e w[e] * src[(start + e) * stride] for one operator row; `src` must have two readable
-// (finite) rows past the last one, because short rows still touch three.
-LCT_DEV float band_dot(const Params& p, const float4* ell, int row, const float* src, int stride) {
+// sum_e w[e] * src[(start + e) * kEllStride] for one operator row; `src` must have two readable
+// (finite) rows past the last one, because short rows still touch three.  The record carries
+// start * kEllStride; rows longer than three continue in the CSR arrays, and the host guarantees
+// (build_tables) that such rows exist only where the caller passes kTail = true.
+template <bool kTail>
+LCT_DEV float band_dot(const Params& p, const float4* ell, int row, const float* src) {
     const float4 e = ell[row];                     // block-local copy in shared memory (warp-uniform: broadcast)
-    const int sl = float_bits(e.x), start = sl & 0xffff, len = sl >> 16;
-    const float* s = src + start * stride;
+    const float* s = src + float_bits(e.x);
     float acc = e.y * s[0];
-    acc = fmaf(e.z, s[stride], acc);
-    acc = fmaf(e.w, s[2 * stride], acc);
-    if (len > 3) {
-        const float* v = p.vals + LCT_LDG(p.rowptr + row);
-        for (int k = 3; k < len; ++k) acc = fmaf(LCT_LDG(v + k), s[k * stride], acc);
+    acc = fmaf(e.z, s[kEllStride], acc);
+    acc = fmaf(e.w, s[2 * kEllStride], acc);
+    if constexpr (kTail) {
+        const int first = LCT_LDG(p.rowptr + row), len = LCT_LDG(p.rowptr + row + 1) - first;
+        if (len > 3) {
+            const float* v = p.vals + first;
+            for (int k = 3; k < len; ++k) acc = fmaf(LCT_LDG(v + k), s[k * kEllStride], acc);
+        }
     }
     return acc;
 }
@@ -233,6 +239,7 @@ LCT_DEV int window_begin(const Params& p, int c) {
 template <class P, int CT_> struct TimeFwd {
     using TwS = TwNone;                        // constant-bank twiddles (a block-local table measured slower here)
     static constexpr int M = P::L, CT = CT_, kThreads = P::TL * CT;
+    static_assert(CT == kEllStride, "the operator records carry offsets for kEllStride-column tiles");
     // phases: load x tile | gather + stage 0 -> zs | stages 1.. in place | post-process
     static constexpr int kPhases = 2 + (P::S - 1) + 1;
     // x tile, FFT buffer and the operator's row records side by side: the register file already caps
@@ -263,23 +270,33 @@ template <class P, int CT_> struct TimeFwd {
             const float4* src = reinterpret_cast<const float4*>(p.in + (size_t)c * p.in_T * NN + col0);
             float4* xs4 = reinterpret_cast<float4*>(smem);
             for (int j = tid; j < M; j += kThreads) reinterpret_cast<float4*>(smem + kWork)[j] = LCT_LDG(p.ell + j);
-            float4 v[(kSlots + kThreads - 1) / kThreads];
+            // slot i = tid + u * kThreads covers row t = i / V4, column quad q = i % V4: q is fixed per
+            // thread and t advances by kThreads / V4 per slot, so the source offset is stepped, not recomputed
+            static_assert(kThreads % V4 == 0, "column quad must be fixed per thread");
+            constexpr int kRowStep = kThreads / V4, kIters = (kSlots + kThreads - 1) / kThreads;
+            const int t0 = tid / V4;
+            ptrdiff_t off = (ptrdiff_t)(t0 - be) * (NN / 4) + tid % V4;
+            const ptrdiff_t off_step = (ptrdiff_t)kRowStep * (NN / 4);
+            float4 v[kIters];
             LCT_UNROLL
-            for (int u = 0; u < (kSlots + kThreads - 1) / kThreads; ++u) {
-                const int i = tid + u * kThreads, t = i / V4, q = i % V4;
+            for (int u = 0; u < kIters; ++u, off += off_step) {
+                const int t = t0 + u * kRowStep;
                 v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t >= be && t < en) v[u] = LCT_LDG(src + (size_t)(t - be) * (NN / 4) + q);
+                if (t >= be && t < en) v[u] = LCT_LDG(src + off);
             }
             LCT_UNROLL
-            for (int u = 0; u < (kSlots + kThreads - 1) / kThreads; ++u) {
+            for (int u = 0; u < kIters; ++u) {
                 const int i = tid + u * kThreads;
                 if (i < kSlots) xs4[i] = v[u];
             }
         } else if constexpr (PH == 1) {
             fwd_stage<P, 0, true, TwS>(tau,
-                [&](int pos, int) {
+                [&](int pos, int slot) {
+                    // rows longer than three taps sit below kTailRows = 2 * st(0): first input of a butterfly only
                     const float4* ell = reinterpret_cast<const float4*>(smem + kWork);
-                    return make_float2(band_dot(p, ell, 2 * pos, xs + col, CT), band_dot(p, ell, 2 * pos + 1, xs + col, CT));
+                    if (slot % P::radix(0) == 0)
+                        return make_float2(band_dot<true>(p, ell, 2 * pos, xs + col), band_dot<true>(p, ell, 2 * pos + 1, xs + col));
+                    return make_float2(band_dot<false>(p, ell, 2 * pos, xs + col), band_dot<false>(p, ell, 2 * pos + 1, xs + col));
                 },
                 [&](int pos, int, float2 v) { zs[pos * CT + col] = v; });
         } else if constexpr (PH < 1 + P::S) {
@@ -291,28 +308,33 @@ template <class P, int CT_> struct TimeFwd {
             // X[k] = Ev + w^k Od and X[M-k] = conj(Ev - w^k Od) from the pair (Z[k], Z[M-k])
             float2* dst = p.s1 + (size_t)c * (M + 1) * NN + col0 + col;
             const float2* zc = zs + col;
-            auto emit = [&](int k, int pos_k, float2* lo, float2* hi) {
+            auto emit = [&](int k, int pos_k, int pos_mk, float2* lo, float2* hi) {
                 const float2 zk = zc[pos_k * CT];
-                const float2 zm = cconj(zc[P::freq_to_pos((M - k) & (M - 1)) * CT]);
+                const float2 zm = cconj(zc[pos_mk * CT]);
                 const float2 ev = cscale(cadd(zk, zm), 0.5f);
                 const float2 d = csub(zk, zm);
                 const float2 od = make_float2(0.5f * d.y, -0.5f * d.x);
                 const float2 t = TwS::mul(od, k * (kTwN / (2 * M)));
                 *lo = cadd(ev, t);
-                if (hi != lo) *hi = cconj(csub(ev, t));
+                if (hi != lo) *hi = cconj(csub(ev, t));       // (a compile-time flag instead of the compare: 6 % slower at M = 128)
             };
-            constexpr int kPairs = (M / 2) / P::TL;                  // k = tau + m*TL < M/2
+            constexpr int kPairs = (M / 2) / P::TL, kBlocks = M / P::TL;        // k = tau + m*TL < M/2
             float2* lo = dst + (size_t)tau * NN;
             float2* hi = dst + (size_t)(M - tau) * NN;
             const size_t step = (size_t)P::TL * NN;
             const int pos_tau = P::freq_to_pos(tau);
+            // position of frequency M - k: for tau > 0, M - k = (kBlocks - 1 - m) TL + (TL - tau), two disjoint
+            // bit fields of the digit reversal (a bit permutation); for tau == 0 it is (kBlocks - m) TL mod M
+            const int pos_neg = P::freq_to_pos((P::TL - tau) & (P::TL - 1));
             LCT_UNROLL
             for (int m = 0; m < kPairs; ++m) {
-                emit(tau + m * P::TL, pos_tau + P::freq_to_pos(m * P::TL), lo, hi);   // disjoint bit fields
+                const int pos_mk = tau != 0 ? pos_neg + P::freq_to_pos((kBlocks - 1 - m) * P::TL)
+                                            : P::freq_to_pos(((kBlocks - m) * P::TL) & (M - 1));
+                emit(tau + m * P::TL, pos_tau + P::freq_to_pos(m * P::TL), pos_mk, lo, hi);   // disjoint bit fields
                 lo += step;
                 hi -= step;
             }
-            if (tau == 0) emit(M / 2, P::freq_to_pos(M / 2), dst + (size_t)(M / 2) * NN, dst + (size_t)(M / 2) * NN);
+            if (tau == 0) emit(M / 2, P::freq_to_pos(M / 2), P::freq_to_pos(M / 2), dst + (size_t)(M / 2) * NN, dst + (size_t)(M / 2) * NN);
         }
     }
 };
@@ -323,6 +345,7 @@ template <class P, int CT_> struct TimeFwd {
 template <class P, int CT_> struct TimeInv {
     using TwS = TwNone;                        // constant-bank twiddles (a block-local table measured slower here)
     static constexpr int M = P::L, CT = CT_, kThreads = P::TL * CT;
+    static_assert(CT == kEllStride, "the operator records carry offsets for kEllStride-column tiles");
     static constexpr int kPhases = 2 + P::S + 1;          // load | stage S-1 -> regs | scatter | middle.. | stage 0 -> vol | gather
     // spectrum tile / FFT buffer (aliased: the first stage goes through registers) + the real volume
     // tile next to it (registers cap the kernel at two blocks per SM anyway; saves a phase)
@@ -352,14 +375,16 @@ template <class P, int CT_> struct TimeInv {
             const float4* src = reinterpret_cast<const float4*>(p.s1 + (size_t)c * (M + 1) * NN + col0);
             float4* zs4 = reinterpret_cast<float4*>(smem);
             for (int j = tid; j < M; j += kThreads) reinterpret_cast<float4*>(smem + kWork)[j] = LCT_LDG(p.ell + j);
-            float4 v[(kSlots + kThreads - 1) / kThreads];
+            static_assert(kThreads % V2 == 0, "column pair must be fixed per thread");
+            constexpr int kIters = (kSlots + kThreads - 1) / kThreads;
+            size_t off = (size_t)(tid / V2) * (NN / 2) + tid % V2;           // stepped per slot, not recomputed
+            const size_t off_step = (size_t)(kThreads / V2) * (NN / 2);
+            float4 v[kIters];
             LCT_UNROLL
-            for (int u = 0; u < (kSlots + kThreads - 1) / kThreads; ++u) {
-                const int i = tid + u * kThreads, k = i / V2, q = i % V2;
-                if (i < kSlots) v[u] = src[(size_t)k * (NN / 2) + q];
-            }
+            for (int u = 0; u < kIters; ++u, off += off_step)
+                if (tid + u * kThreads < kSlots) v[u] = src[off];
             LCT_UNROLL
-            for (int u = 0; u < (kSlots + kThreads - 1) / kThreads; ++u) {
+            for (int u = 0; u < kIters; ++u) {
                 const int i = tid + u * kThreads;
                 if (i < kSlots) zs4[i] = v[u];
             }
@@ -403,10 +428,12 @@ template <class P, int CT_> struct TimeInv {
             const float* vc = vol + col;
             const float4* ell = reinterpret_cast<const float4*>(smem + kWork);
             if (p.minmax_keys == nullptr) {
+                const float4* er = ell + be + tau;         // mtxi rows have at most three entries: no tail
 #ifndef LCT_EMULATE
-#pragma unroll 4
+#pragma unroll 8                                   // full unrolling (16) measured 2 % slower at M = 256
 #endif
-                for (int j = tau; j < p.out_T; j += P::TL, d += step) *d = band_dot(p, ell, be + j, vc, CT);
+                for (int m = 0; m < M / P::TL; ++m, d += step)
+                    if (tau + m * P::TL < p.out_T) *d = band_dot<false>(p, er, m * P::TL, vc);
             } else {
                 float mn = 3.4e38f, mx = -3.4e38f;
                 int jmn = 0, jmx = 0;
@@ -414,7 +441,7 @@ template <class P, int CT_> struct TimeInv {
 #pragma unroll 4
 #endif
                 for (int j = tau; j < p.out_T; j += P::TL, d += step) {
-                    const float v = band_dot(p, ell, be + j, vc, CT);
+                    const float v = band_dot<false>(p, ell, be + j, vc);
                     *d = v;
                     if (v < mn) { mn = v; jmn = j; }
                     if (v > mx) { mx = v; jmx = j; }

@@ -5,9 +5,12 @@
 // (/root/reference/models/tflct.py:135-138,156-159).  Both are staircase band matrices
 // (utils/helper.py:35-69): every row is one contiguous run of columns, nearly always of
 // length <= 3.  Each row is therefore stored as one 16-byte record
-//     { start | (len << 16),  w0, w1, w2 }
-// read with a single 128-bit load and applied branch-free; only the few longer rows
-// (the first ~sqrt(M) rows of mtx) continue into the CSR value array.
+//     { start * kEllStride,  w0, w1, w2 }
+// read with a single 128-bit load and applied branch-free (kEllStride = columns per time tile,
+// so the first field is directly the element offset into the tile).  Only the few longer rows
+// (the first ~sqrt(M) rows of mtx) continue into the CSR arrays; build_tables checks that they
+// all lie below `tail_rows`, the only rows for which the time-forward kernel looks for a tail,
+// and that mtxi = mtx^T has none.
 #pragma once
 
 #include <cstdint>
@@ -17,7 +20,9 @@
 
 namespace lct {
 
-struct EllRow { int32_t start_len; float w[3]; };   // 16 bytes, loaded as float4
+constexpr int kEllStride = 32;                        // == TimeTile::CT (static_assert in the kernels)
+
+struct EllRow { int32_t offset; float w[3]; };       // 16 bytes, loaded as float4
 
 struct HostTables {
     int M = 0;
@@ -36,7 +41,7 @@ inline std::vector<EllRow> make_ell(int M, const std::vector<int32_t>& rowptr, c
     std::vector<EllRow> ell(M);
     for (int i = 0; i < M; ++i) {
         const int len = rowptr[i + 1] - rowptr[i];
-        ell[i].start_len = (len > 0 ? start[i] : 0) | (len << 16);
+        ell[i].offset = (len > 0 ? start[i] : 0) * kEllStride;
         for (int e = 0; e < 3; ++e) ell[i].w[e] = (e < len) ? vals[rowptr[i] + e] : 0.0f;
     }
     return ell;
@@ -44,7 +49,7 @@ inline std::vector<EllRow> make_ell(int M, const std::vector<int32_t>& rowptr, c
 
 // Returns "" on success, otherwise a description of what is wrong with the operator.
 inline std::string build_tables(int M, const int32_t* rowptr, const int32_t* colidx, const float* vals,
-                                const float* falloff /* M or null */, HostTables& t) {
+                                const float* falloff /* M or null */, int tail_rows, HostTables& t) {
     t.M = M;
     if (rowptr[0] != 0) return "CSR row pointers must start at 0";
     const int nnz = rowptr[M];
@@ -64,6 +69,11 @@ inline std::string build_tables(int M, const int32_t* rowptr, const int32_t* col
             t_last[j] = i;
             t_count[j]++;
         }
+    }
+    for (int i = 0; i < M; ++i) {
+        if (rowptr[i + 1] - rowptr[i] > 3 && i >= tail_rows)
+            return "operator rows with more than 3 entries must be among the first " + std::to_string(tail_rows) + " rows";
+        if (t_count[i] > 3) return "operator columns must have at most 3 entries";
     }
     t.mtx_rowptr.assign(rowptr, rowptr + M + 1);
     t.mtx_vals.assign(vals, vals + nnz);

@@ -79,7 +79,7 @@ int lct_emu_run(int M, int N, int C, int D, int Tin, int be_uniform, const int* 
                 const int* mtx_rowptr, const int* mtx_colidx, const float* mtx_vals, const float* falloff,
                 const float* filt, const float* filt_plane, int backward, int mask) {
     lct::HostTables ht;
-    if (!lct::build_tables(M, mtx_rowptr, mtx_colidx, mtx_vals, falloff, ht).empty()) return 100;
+    if (!lct::build_tables(M, mtx_rowptr, mtx_colidx, mtx_vals, falloff, lct::time_tail_rows(M), ht).empty()) return 100;
     auto band = [](const std::vector<lct::EllRow>& e, const std::vector<int32_t>& rp, const std::vector<float>& v) {
         return lct::BandTable{reinterpret_cast<const float4*>(e.data()), rp.data(), v.data()};
     };
