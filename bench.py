@@ -296,7 +296,7 @@ def main():
     streamer = hp.LctStreamer(layer, tbes, tens, depth=2)
     streamer.run([x_hosts[i % n_buf] for i in range(W)], [y_hosts[i % n_buf] for i in range(W)])
     e2e_runs = []
-    for _ in range(3):                      # host-side jitter (other tenants on the PCIe switch) is large: median of 3
+    for _ in range(5):                      # host-side jitter (other tenants on the PCIe switch) is large: median of 5
         barrier()
         t0 = time.perf_counter()
         streamer.run([x_hosts[i % n_buf] for i in range(K)], [y_hosts[i % n_buf] for i in range(K)])
@@ -306,6 +306,24 @@ def main():
     e2e_ms = statistics.median(e2e_runs)
     e2e_value = world * B * K / (e2e_ms * 1e-3)
     e2e_ok = bool(torch.equal(y_hosts[(K - 1) % n_buf], y.cpu()))
+
+    # ---- what the link allows: the same bytes copied both ways at once with no compute in between ----
+    scratch_y = torch.empty_like(y)
+    c_in, c_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    link_runs = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            with torch.cuda.stream(c_in):
+                x.copy_(x_hosts[i % n_buf], non_blocking=True)
+            with torch.cuda.stream(c_out):
+                y_hosts[i % n_buf].copy_(scratch_y, non_blocking=True)
+        torch.cuda.synchronize()
+        link_runs.append(sharding.max_over_ranks((time.perf_counter() - t0) * 1e3, dev))
+    link_ms = statistics.median(link_runs)
+    link_gbs = x.numel() * 4 * K / (link_ms * 1e-3) / 1e9          # per direction, per GPU
+    del scratch_y
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -348,9 +366,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": "transients/s", "h2d_bytes_per_step": x.numel() * 4,
                     "d2h_bytes_per_step": y.numel() * 4,
                     "matches_device_path": e2e_ok,
+                    "link": {"what": "same host buffers copied H2D and D2H concurrently, no compute: the PCIe ceiling of this step",
+                             "gbs_per_direction": link_gbs, "ms_per_step": link_ms / K,
+                             "e2e_fraction_of_link": link_ms / e2e_ms},
                     "how": "LctStreamer public API: pinned x -> H2D -> lct.forward -> D2H of the whole volume for every "
                            "step; upload/transform/download of consecutive steps overlap on three streams; host wall "
-                           "clock from first upload to last byte landed; median of 3 runs of K steps",
+                           "clock from first upload to last byte landed; median of 5 runs of K steps",
                     "runs_ms": e2e_runs, "host_bound_to_gpu_numa_node": numa_bound},
             "gpu_launches": n_kernels * K,
             "fwd_bwd": {"value": world * B * K / (fb_ms * 1e-3), "unit": "transients/s", "ms_per_step": fb_ms / K,

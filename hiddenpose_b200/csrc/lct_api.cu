@@ -2,6 +2,7 @@
 // Host side only: plan construction, workspace carving, kernel launches.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -86,7 +87,7 @@ struct GpuLauncher {
         if (events && err == cudaSuccess) err = cudaEventRecord((cudaEvent_t)events[i], stream);
     }
     template <class K> int launch(const lct::Params& p) {
-        static bool attr_set[kMaxDevices] = {};
+        static std::atomic<bool> attr_set[kMaxDevices] = {};
         auto kern = lct::lct_kernel<K>;
         if (!attr_set[device]) {
             if (K::kSmem > 48 * 1024) {
@@ -421,9 +422,13 @@ int lct_forward_minmax(const lct_plan* plan, const float* x, const int32_t* tbe,
                static_cast<unsigned long long*>(minmax_keys));
 }
 
-static unsigned reduce_blocks(long long elems) {
-    long long b = (elems / 4 + 255) / 256;
-    return (unsigned)(b < 1 ? 1 : (b > 64 ? 64 : b));
+// blocks per channel for the grid-stride passes: about one full wave of 256-thread blocks (8 per SM on
+// 148 SMs) over all channels, never more blocks than there are 128-bit loads to share out
+static unsigned reduce_blocks(long long elems, int channels) {
+    const long long work = (elems / 4 + 255) / 256;
+    long long b = (8 * 148 + channels - 1) / channels;
+    if (b > work) b = work;
+    return (unsigned)(b < 1 ? 1 : b);
 }
 
 int lct_minmax(const float* x, int32_t channels, int64_t elems, void* keys, void* stream_) {
@@ -431,7 +436,7 @@ int lct_minmax(const float* x, int32_t channels, int64_t elems, void* keys, void
         return fail(LCT_ERR_INVALID, "bad argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     LCT_CUDA(cudaMemsetAsync(keys, 0xFF, (size_t)channels * 2 * sizeof(unsigned long long), stream));
-    lct::minmax_kernel<<<dim3(reduce_blocks(elems), channels), 256, 0, stream>>>(x, static_cast<unsigned long long*>(keys), elems);
+    lct::minmax_kernel<<<dim3(reduce_blocks(elems, channels), channels), 256, 0, stream>>>(x, static_cast<unsigned long long*>(keys), elems);
     LCT_CUDA(cudaGetLastError());
     return LCT_OK;
 }
@@ -440,7 +445,7 @@ int lct_normalize_feature(const float* x, const void* keys, float* out, int32_t 
                           float scale, void* stream_) {
     if (!x || !keys || !out || channels <= 0 || elems <= 0 || (((uintptr_t)x | (uintptr_t)out) & 15))
         return fail(LCT_ERR_INVALID, "bad argument");
-    lct::normalize_kernel<<<dim3(reduce_blocks(elems), channels), 256, 0, (cudaStream_t)stream_>>>(
+    lct::normalize_kernel<<<dim3(reduce_blocks(elems, channels), channels), 256, 0, (cudaStream_t)stream_>>>(
         x, out, static_cast<const unsigned long long*>(keys), elems, scale);
     LCT_CUDA(cudaGetLastError());
     return LCT_OK;
@@ -451,7 +456,7 @@ int lct_normalize_feature_backward(const float* x, const float* gout, const void
     if (!x || !gout || !keys || !gx || !sums || channels <= 0 || elems <= 0) return fail(LCT_ERR_INVALID, "bad argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     LCT_CUDA(cudaMemsetAsync(sums, 0, (size_t)channels * 2 * sizeof(double), stream));
-    const dim3 grid(reduce_blocks(elems), channels);
+    const dim3 grid(reduce_blocks(elems, channels), channels);
     lct::normalize_bwd_sums_kernel<<<grid, 256, 0, stream>>>(x, gout, static_cast<const unsigned long long*>(keys),
                                                              static_cast<double*>(sums), elems);
     lct::normalize_bwd_kernel<<<grid, 256, 0, stream>>>(gout, gx, static_cast<const unsigned long long*>(keys),
