@@ -9,7 +9,7 @@ from ._native import build_native, load as load_native          # noqa: F401
 from .feature_extraction import FeatureExtraction, skip_sum      # noqa: F401
 from .feature_propagation import LCT, FeaturePropagation, VisibleNet, normalize, normalize_feature   # noqa: F401
 from .lct_function import LctFunction, LctPlan                   # noqa: F401
-from .streaming import LctStreamer                               # noqa: F401
+from .streaming import LctGraph, LctStreamer                               # noqa: F401
 from .tflct import lct                                           # noqa: F401
 
 __all__ = ["lct", "LCT", "FeaturePropagation", "VisibleNet", "normalize", "normalize_feature",

@@ -92,3 +92,47 @@ class LctStreamer:
                 slot["drained"].record(self.s_out)
         self.s_out.synchronize()
         return y_hosts
+
+
+class LctGraph:
+    """One-launch replay of the layer for a fixed shape and window (CUDA graph).
+
+    A single transient keeps a B200 busy for a few tens of microseconds -- less than the host needs to
+    issue the layer's kernels one by one -- so a latency-bound caller (one transient per frame, as in
+    /root/reference/models/test_tflct.py:84-95) captures the forward once and replays it:
+    ``g = LctGraph(layer, (1, 1, T, N, N), tbes, tens); y = g(x)``.  The library neither allocates
+    nor synchronises inside ``lct_forward``, which is what makes the capture legal.  ``y`` is a static
+    buffer overwritten by the next call; inference only (no autograd through a replay).
+    """
+
+    def __init__(self, layer, shape, tbes, tens, normalize: bool = False):
+        inner = layer.method if isinstance(getattr(layer, "method", None), torch.nn.Module) else layer
+        if getattr(inner, "_plan", None) is None:
+            raise RuntimeError("LctGraph needs a layer that was moved to a CUDA device with todev()")
+        self.device = inner._plan.device
+        self.x = torch.zeros(tuple(shape), dtype=torch.float32, device=self.device)
+        tbes, tens = list(tbes), list(tens)
+
+        def body():
+            y = layer(self.x, tbes, tens)
+            if normalize:
+                from .feature_propagation import normalize_feature
+                y = normalize_feature(y)
+            return y
+
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.no_grad(), torch.cuda.stream(side):
+            body()                                              # warm up outside the capture (workspace, attributes)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.y = body()
+
+    def __call__(self, x):
+        if x.shape != self.x.shape:
+            raise ValueError(f"LctGraph was captured for shape {tuple(self.x.shape)}, got {tuple(x.shape)}")
+        self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.y

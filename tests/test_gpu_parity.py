@@ -291,6 +291,25 @@ def test_cuda_graph_capture_replays_the_layer():
             assert torch.equal(static_y, layer(fresh, [0] * B, [M] * B))
 
 
+def test_lct_graph_replays_layer_and_normalize():
+    """hiddenpose_b200.LctGraph: one-launch replay (layer, or layer + normalize_feature) equals the eager calls."""
+    import hiddenpose_b200 as hp
+    M, N = 64, 32
+    fp = hp.FeaturePropagation(image_size=N, time_size=M, bin_len=0.08, wall_size=2.0, dnum=1, dev="cuda:0")
+    x = torch.rand(1, 1, M - 4, N, N, device="cuda")
+    tb, te = [2], [M - 2]
+    g_plain = hp.LctGraph(fp, x.shape, tb, te)
+    g_norm = hp.LctGraph(fp, x.shape, tb, te, normalize=True)
+    with torch.no_grad():
+        for _ in range(2):
+            x = torch.rand_like(x)
+            want = fp(x, tb, te)
+            assert torch.equal(g_plain(x), want)
+            assert torch.equal(g_norm(x), hp.normalize_feature(fp(x, tb, te)))
+    with pytest.raises(ValueError):
+        g_plain(torch.rand(2, 1, M - 4, N, N, device="cuda"))
+
+
 @pytest.mark.parametrize("M,N,method", [(64, 16, "lct"), (128, 64, "lct"), (64, 128, "lct"), (64, 32, "bp")])
 def test_device_built_filter_matches_host_built(M, N, method, monkeypatch):
     """Row f3: the filter built on the GPU from the PSF support gives the same volumes as the one built on
