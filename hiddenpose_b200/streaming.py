@@ -127,7 +127,8 @@ class LctGraph:
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self.graph):
+        # thread_local: CUDA calls made by other threads meanwhile (e.g. a process group's watchdog) must not break the capture
+        with torch.no_grad(), torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.y = body()
 
     def __call__(self, x):

@@ -141,3 +141,22 @@ def test_emulated_kernels_have_no_intra_phase_races():
     orc = O.LctOracle(8, 32, 0.16)
     yo = orc.forward(torch.from_numpy(x).view(3, 1, 25, 8, 8), [0, 3, 7], [25, 28, 32]).numpy().reshape(3, 32, 8, 8)
     assert O.rel_l2(a, yo) <= 1e-5
+
+
+def test_operator_structure_is_validated():
+    """The kernels look for rows longer than three taps only among the first few rows of mtx and never in
+    mtx^T (lct_tables.h); an operator that breaks this must be refused, not silently truncated."""
+    from tests.emu.emu import EmuPlan
+    plan = EmuPlan(8, 32, 0.16)
+    x = np.random.RandomState(2).rand(1, 32, 8, 8).astype(np.float32)
+    plan.run(x, 1, 32, [0])                                   # the reference operator is accepted
+    rp, ci, v = (a.copy() for a in plan.csr)
+    # stretch the last row to five contiguous entries: a long row far outside the allowed head
+    last = np.arange(27, 32, dtype=np.int32)
+    ci2 = np.concatenate([ci[:rp[31]], last]).astype(np.int32)
+    v2 = np.concatenate([v[:rp[31]], np.full(5, 0.2, np.float32)]).astype(np.float32)
+    rp2 = rp.copy()
+    rp2[32] = rp2[31] + 5
+    plan.csr = (rp2, ci2, v2)
+    with pytest.raises(AssertionError):
+        plan.run(x, 1, 32, [0])                               # lct_emu_run returns 100 when build_tables refuses
