@@ -131,6 +131,27 @@ def cpu_oracle_rate(M, N, reps, warm, threads=None):
     return times
 
 
+def library_port_rate(M, N, B, dev, reps=10, warm=3):
+    """ms per forward of the same oracle port run on the GPU through torch (cuFFT + dense cuBLAS matmuls, the
+    strongest pre-existing implementation of the reference's op sequence) -- a second baseline
+    reported beside the CPU one, never the product path."""
+    from oracle.lct_oracle import LctOracle
+    orc = LctOracle(N, M, bin_len_for(M))
+    torch.manual_seed(410)
+    x = torch.rand(B, 1, M, N, N, device=dev)
+    evs = []
+    with torch.no_grad():
+        for i in range(warm + reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            orc.forward(x, [0] * B, [M] * B)
+            b.record()
+            if i >= warm:
+                evs.append((a, b))
+    torch.cuda.synchronize()
+    return statistics.median(a.elapsed_time(b) for a, b in evs)
+
+
 def run_reference(args, rank, out):
     """`--impl reference`: the reference's own CPU implementation of the path (the oracle port:
     /root/reference cannot travel to the GPU box) on the host cores; rank 0 only."""
@@ -430,6 +451,15 @@ def main():
                 "kind": "port",
                 "sample": f"{args.cpu_reps} forwards of one 1x1x{M}x{N}x{N} transient (oracle port of tflct.py:94-179, "
                           f"torch CPU fp32), median; host has {os.cpu_count()} logical cores"}
+            try:
+                port_ms = library_port_rate(M, N, B, dev)
+                line["cpu_baseline"]["same_port_on_gpu_via_torch"] = {
+                    "value": B / (port_ms * 1e-3), "unit": "transients/s", "ms_per_step": port_ms,
+                    "what": "the same oracle port (reference op sequence) on this B200 through torch: cuFFT fftn/ifftn, "
+                            "dense cuBLAS matmuls for the resampling, fp32, whole batch, median of 10"}
+            except Exception as exc:                     # out of memory at the large shapes: report and move on
+                line["cpu_baseline"]["same_port_on_gpu_via_torch"] = {"unavailable": repr(exc)[:200]}
+                torch.cuda.synchronize()
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
