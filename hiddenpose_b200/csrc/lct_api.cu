@@ -83,6 +83,7 @@ struct GpuLauncher {
     int device;
     cudaError_t err = cudaSuccess;
     void* const* events = nullptr;          // optional: 6 cudaEvent_t recorded around the stages
+    int prefetch_ahead = 0;                 // SM count when the time kernels should warm L2 for later blocks, else 0
     void mark(int i) {
         if (events && err == cudaSuccess) err = cudaEventRecord((cudaEvent_t)events[i], stream);
     }
@@ -101,7 +102,9 @@ struct GpuLauncher {
         }
         int gx, gy;
         K::grid(p, gx, gy);
-        kern<<<dim3(gx, gy), K::kThreads, K::kSmem, stream>>>(p, K::iterations(p));
+        lct::Params q = p;
+        q.ahead = prefetch_ahead > 0 ? prefetch_ahead * K::kMinBlocks : 0;      // resident blocks of this kernel
+        kern<<<dim3(gx, gy), K::kThreads, K::kSmem, stream>>>(q, K::iterations(p));
         err = cudaGetLastError();
         return err == cudaSuccess ? 0 : 1;
     }
@@ -177,6 +180,7 @@ struct lct_plan {
     // kernel overlaps the next kernel of another group (the chains differ in what bounds them).
     static constexpr int kMaxGroups = 8;
     int groups = 1;
+    int prefetch_ahead = 0;                 // SM count, or 0 when LCT_L2_PREFETCH=0 (see GpuLauncher::prefetch_ahead)
     cudaStream_t side[kMaxGroups] = {};
     cudaEvent_t fork = nullptr, join[kMaxGroups] = {};
     mutable std::mutex side_mutex;          // the side streams/events are shared by all callers of the plan
@@ -303,6 +307,12 @@ int lct_plan_create(const lct_desc* d, lct_plan** out) {
     }
 #undef LCT_TRY
     {
+        const char* pf = std::getenv("LCT_L2_PREFETCH");
+        int sms = 0;
+        if ((!pf || std::atoi(pf) != 0) && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->device) == cudaSuccess)
+            p->prefetch_ahead = sms;
+    }
+    {
         const char* env = std::getenv("LCT_STREAM_GROUPS");
         int g = env ? std::atoi(env) : LCT_DEFAULT_STREAM_GROUPS;
         p->groups = g < 1 ? 1 : (g > lct_plan::kMaxGroups ? lct_plan::kMaxGroups : g);
@@ -379,6 +389,7 @@ static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const 
             cudaStream_t sg = g == 0 ? stream : plan->side[g];
             if (g) LCT_CUDA(cudaStreamWaitEvent(sg, plan->fork, 0));
             GpuLauncher lg{sg, plan->device};
+            lg.prefetch_ahead = plan->prefetch_ahead;
             const int rc = lct::run_chain(lg, t, M, N, (int)(c1 - c0), D, Tin, tbe[0], be_dev, (int)c0,
                                           in + (size_t)c0 * in_stride, out + (size_t)c0 * out_stride,
                                           s1 + (size_t)c0 * (M + 1) * N * N, s2 + (size_t)c0 * (M + 1) * 2 * N * N, backward,
@@ -392,6 +403,7 @@ static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const 
     }
     GpuLauncher l{stream, plan->device};
     l.events = events;
+    l.prefetch_ahead = plan->prefetch_ahead;
     for (long long c0 = 0; c0 < C; c0 += chunk) {
         const int cn = (int)((C - c0 < chunk) ? (C - c0) : chunk);
         const int rc = lct::run_chain(l, t, M, N, cn, D, Tin, tbe[0], be_dev, (int)c0,

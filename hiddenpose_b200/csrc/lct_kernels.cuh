@@ -179,7 +179,18 @@ struct Params {
     // optional (K5, forward): per-channel {min key, complemented max key} of the volume it writes, reduced
     // with atomicMin while the values are still in registers (lct_normalize.cuh); pre-set to all ones
     unsigned long long* minmax_keys;
+    // time kernels: how many blocks ahead (in launch order) the tile to warm in L2 lies; 0 = no prefetch.
+    // The launcher sets it to the number of resident blocks, so the lines arrive about one block life early.
+    int ahead;
 };
+
+LCT_DEV void prefetch_l2(const void* ptr) {
+#ifndef LCT_EMULATE
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+#else
+    (void)ptr;
+#endif
+}
 
 // order-preserving key of a float and its position (see lct_normalize.cuh)
 LCT_DEV unsigned long long minmax_key(float v, unsigned int pos, bool is_max) {
@@ -284,6 +295,16 @@ template <class P, int CT_> struct TimeFwd {
                 v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (t >= be && t < en) v[u] = LCT_LDG(src + off);
             }
+            if (p.ahead > 0) {
+                // own loads are in flight: ask L2 for the tile of the block that will run here about one block life later
+                const int gx = NN / CT;
+                const long long next = (long long)by * gx + bx + p.ahead;
+                const int nc = (int)(next / gx), nb = (int)(next % gx);
+                if (nc < p.C) {
+                    const float* ns = p.in + (size_t)nc * p.in_T * NN + (size_t)nb * CT;     // one 128-byte line per time bin
+                    for (int t = tid; t < p.in_T; t += kThreads) prefetch_l2(ns + (size_t)t * NN);
+                }
+            }
             LCT_UNROLL
             for (int u = 0; u < kIters; ++u) {
                 const int i = tid + u * kThreads;
@@ -383,6 +404,16 @@ template <class P, int CT_> struct TimeInv {
             LCT_UNROLL
             for (int u = 0; u < kIters; ++u, off += off_step)
                 if (tid + u * kThreads < kSlots) v[u] = src[off];
+            if (p.ahead > 0) {
+                const int gx = NN / CT;
+                const long long next = (long long)by * gx + bx + p.ahead;
+                const int nc = (int)(next / gx), nb = (int)(next % gx);
+                if (nc < p.C) {
+                    const char* ns = reinterpret_cast<const char*>(p.s1 + (size_t)nc * (M + 1) * NN + (size_t)nb * CT);
+                    for (int i = tid; i < 2 * (M + 1); i += kThreads)                       // two 128-byte lines per frequency
+                        prefetch_l2(ns + (size_t)(i >> 1) * NN * sizeof(float2) + (i & 1) * 128);
+                }
+            }
             LCT_UNROLL
             for (int u = 0; u < kIters; ++u) {
                 const int i = tid + u * kThreads;
