@@ -513,6 +513,18 @@ template <class P, int CT_> struct RowFwd {
         auto ld_s = [&](int pos, int) { return zs[pos * CT + col]; };
         auto st_s = [&](int pos, int, float2 v) { zs[pos * CT + col] = v; };
         auto st_g = [&](int pos, int slot, float2 v) { dst[(size_t)P::template freq_of<P::S - 1>(pos, slot) * N] = v; };
+        if constexpr (PH == 0) {
+            if (p.ahead > 0) {       // warm L2 with the (plane, column tile) of the block one residency ahead
+                const int gx = N / CT;
+                const long long next = (long long)by * gx + bx + p.ahead;
+                if (next / gx < (long long)p.C * (p.M + 1)) {
+                    const char* ns = reinterpret_cast<const char*>(p.s1 + (size_t)(next / gx) * N * N + (size_t)(next % gx) * CT);
+                    constexpr int kLines = (CT * (int)sizeof(float2) + 127) / 128;
+                    for (int i = tid; i < N * kLines; i += kThreads)
+                        prefetch_l2(ns + (size_t)(i / kLines) * N * sizeof(float2) + (i % kLines) * 128);
+                }
+            }
+        }
         if constexpr (P::S == 1) {
             fwd_stage<P, 0, true, TwS>(tau, ld_g, st_g);
         } else if constexpr (PH == 0) {
@@ -553,6 +565,18 @@ template <class P, int CT_> struct RowInv {
         auto ld_s = [&](int pos, int) { return zs[pos * CT + col]; };
         auto st_s = [&](int pos, int, float2 v) { zs[pos * CT + col] = v; };
         auto st_g = [&](int pos, int, float2 v) { dst[(size_t)pos * N] = v; };
+        if constexpr (PH == 0) {
+            if (p.ahead > 0) {
+                const int gx = N / CT;
+                const long long next = (long long)by * gx + bx + p.ahead;
+                if (next / gx < (long long)p.C * (p.M + 1)) {
+                    const char* ns = reinterpret_cast<const char*>(p.s2 + (size_t)(next / gx) * L * N + (size_t)(next % gx) * CT);
+                    constexpr int kLines = (CT * (int)sizeof(float2) + 127) / 128;
+                    for (int i = tid; i < L * kLines; i += kThreads)
+                        prefetch_l2(ns + (size_t)(i / kLines) * N * sizeof(float2) + (i % kLines) * 128);
+                }
+            }
+        }
         if constexpr (P::S == 1) {
             inv_stage<P, 0, true, TwS>(tau, ld_g, st_g);
         } else if constexpr (PH == 0) {
@@ -612,6 +636,19 @@ template <class P, int RB_> struct ColFilter {
         const size_t chan = (size_t)(p.M + 1) * L * N;
         float2* row = p.s2 + (size_t)c * chan + ((size_t)kt * L + kh) * N;
         if constexpr (PH == 0) {
+            if (it == 0 && p.ahead > 0) {
+                // warm L2 with channel 0's rows and the filter rows of the block one residency ahead
+                const int gx = L / RB;
+                const long long next = (long long)by * gx + bx + p.ahead;
+                if (next / gx <= p.M) {
+                    const size_t first = (size_t)(next / gx) * L + (size_t)(next % gx) * RB;          // kt * L + kh
+                    const char* rows = reinterpret_cast<const char*>(p.s2 + first * N);
+                    const char* filt = reinterpret_cast<const char*>(p.filt + first * L);
+                    constexpr int kRowLines = RB * N * (int)sizeof(float2) / 128, kFiltLines = RB * L * (int)sizeof(float2) / 128;
+                    for (int i = tid; i < kRowLines; i += kThreads) prefetch_l2(rows + (size_t)i * 128);
+                    for (int i = tid; i < kFiltLines; i += kThreads) prefetch_l2(filt + (size_t)i * 128);
+                }
+            }
             if (it == 0) {
                 fetch(row, tau, r);
                 const float2* f = p.filt + ((size_t)kt * L + kh) * L;
