@@ -100,11 +100,11 @@ struct GpuLauncher {
             if (err != cudaSuccess) return 1;
             attr_set[device] = true;
         }
-        int gx, gy;
-        K::grid(p, gx, gy);
         lct::Params q = p;
         q.ahead = prefetch_ahead > 0 ? prefetch_ahead * K::kMinBlocks : 0;      // resident blocks of this kernel
-        kern<<<dim3(gx, gy), K::kThreads, K::kSmem, stream>>>(q, K::iterations(p));
+        int gx, gy;
+        K::grid(q, gx, gy);
+        kern<<<dim3(gx, gy), K::kThreads, K::kSmem, stream>>>(q, K::iterations(q));
         err = cudaGetLastError();
         return err == cudaSuccess ? 0 : 1;
     }

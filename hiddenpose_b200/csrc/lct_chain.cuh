@@ -65,7 +65,11 @@ constexpr bool supported_N(int N) { return N == 8 || N == 16 || N == 32 || N == 
 enum ChainStage { kStageTimeFwd = 1, kStageRowFwd = 2, kStageColFilter = 4, kStageRowInv = 8, kStageTimeInv = 16, kStageAll = 31 };
 
 template <int M, class Launcher> int launch_time_fwd(const Params& p, Launcher& l) {
-    return l.template launch<TimeFwd<typename TimeFwdPlan<M>::type, TimeTile<M>::CT>>(p);
+    using P = typename TimeFwdPlan<M>::type;
+    if constexpr (P::E >= 32)           // one block per SM: persistent blocks with the next tile copied ahead
+        return l.template launch<TimeFwdPersistent<P, TimeTile<M>::CT>>(p);
+    else
+        return l.template launch<TimeFwd<P, TimeTile<M>::CT>>(p);
 }
 template <int M, class Launcher> int launch_time_inv(const Params& p, Launcher& l) {
     return l.template launch<TimeInv<typename TimeInvPlan<M>::type, TimeTile<M>::CT>>(p);

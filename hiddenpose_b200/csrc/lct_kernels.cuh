@@ -192,6 +192,50 @@ LCT_DEV void prefetch_l2(const void* ptr) {
 #endif
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS); `valid` false zero-fills the 16 bytes instead.
+// The emulator copies at issue time, one legal outcome of the asynchronous copy.
+LCT_DEV void cp_async16(void* dst_smem, const void* src, bool valid) {
+#ifndef LCT_EMULATE
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+#else
+    if (valid) std::memcpy(dst_smem, src, 16); else std::memset(dst_smem, 0, 16);
+#endif
+}
+LCT_DEV void cp_async_commit() {
+#ifndef LCT_EMULATE
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+LCT_DEV void cp_async_wait_all() {
+#ifndef LCT_EMULATE
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
+// Persistent tile walk of the time kernels: min(tiles, resident blocks) blocks, block b walks tiles b, b + G, ...
+// and copies tile i + 1 into shared memory (cp.async) while it still works on tile i.  K5 always runs this way;
+// K1 only at one block per SM (M = 512) -- at two or more blocks per SM the plain loads with the L2 warm-up of a
+// later block's tile measured faster (cfg2 38.0 vs 40.7 us, cfg4 91 vs 92 us, cfg3 280 vs 253 us).
+// N is a power of two, so is the number of tiles per channel: split a tile index with a shift and a mask
+LCT_DEV int ilog2_pow2(int v) {
+#ifndef LCT_EMULATE
+    return 31 - __clz(v);
+#else
+    return __builtin_ctz((unsigned)v);
+#endif
+}
+
+struct TileWalk {
+    int total, G;
+    LCT_HD TileWalk(const Params& p, int tiles_per_channel, bool persist = true) {
+        total = tiles_per_channel * p.C;
+        G = (persist && p.ahead > 0 && p.ahead < total) ? p.ahead : total;
+    }
+    LCT_HD int iterations() const { return (total + G - 1) / G; }
+};
+
 // order-preserving key of a float and its position (see lct_normalize.cuh)
 LCT_DEV unsigned long long minmax_key(float v, unsigned int pos, bool is_max) {
     const unsigned int b = (unsigned int)float_bits(v);
@@ -360,6 +404,162 @@ template <class P, int CT_> struct TimeFwd {
     }
 };
 
+// K1, persistent form (used at one block per SM, M = 512): same phases as TimeFwd, but min(tiles, resident)
+// blocks walk the tiles and the next tile's rows are copied into xs (cp.async) during the in-place stages.
+// Kept as a separate type so that the one-tile-per-block kernel above compiles exactly as before: at
+// M <= 256 its code generation is sensitive enough that sharing the source cost it up to 10 %.
+template <class P, int CT_> struct TimeFwdPersistent {
+    using TwS = TwNone;                        // constant-bank twiddles (a block-local table measured slower here)
+    static constexpr int M = P::L, CT = CT_, kThreads = P::TL * CT;
+    static_assert(CT == kEllStride, "the operator records carry offsets for kEllStride-column tiles");
+    // phases: load x tile | gather + stage 0 -> zs | stages 1.. in place | post-process
+    static constexpr int kPhases = 2 + (P::S - 1) + 1;
+    // x tile, FFT buffer and the operator's row records side by side: the register file already caps
+    // the kernel at two blocks per SM, so nothing is gained by aliasing them (and a phase is saved)
+    static constexpr size_t kXs = ((size_t)(M + 2) * CT * sizeof(float) + 15) / 16 * 16;
+    static constexpr size_t kWork = kXs + (size_t)M * CT * sizeof(float2);
+    static constexpr size_t kSmem = TwS::kBytes + (kWork + (size_t)M * sizeof(float4));
+    static constexpr bool kWarpSync = false;
+    // 1024 threads/SM at <= 64 regs; the 32-wide butterflies need 128 regs (512 threads/SM)
+    static constexpr int kMinBlocks = (P::E >= 32) ? (512 / kThreads > 0 ? 512 / kThreads : 1) : ((kThreads >= 1024) ? 1 : 1024 / kThreads);
+    struct Regs {};
+    static constexpr bool kPersist = true;
+    static void grid(const Params& p, int& gx, int& gy) {
+        if (kPersist) { gx = TileWalk(p, p.N * p.N / CT).G; gy = 1; }
+        else { gx = p.N * p.N / CT; gy = p.C; }              // one tile per block: (column tile, channel)
+    }
+    static int iterations(const Params& p) { return kPersist ? TileWalk(p, p.N * p.N / CT).iterations() : 1; }
+
+    static constexpr bool kHasPrologue = true;
+    static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwS::fill(smem, tid, kThreads); }
+
+    // x tile -> xs[(M+2)][CT] f32 by 16-byte asynchronous copies, zero-filled outside the window [be, en) and in
+    // the two pad rows.  Slot i = tid + u * kThreads covers row i / V4, column quad i % V4: the quad is fixed per
+    // thread and the row advances by kThreads / V4 per slot, so the source offset is stepped, not recomputed.
+    static LCT_DEV void issue_tile(const Params& p, unsigned char* smem, int tid, int tile) {
+        constexpr int V4 = CT / 4, kSlots = (M + 2) * V4;
+        static_assert(kThreads % V4 == 0, "column quad must be fixed per thread");
+        constexpr int kRowStep = kThreads / V4, kIters = (kSlots + kThreads - 1) / kThreads;
+        const int NN = p.N * p.N, tpc = NN / CT, c = tile >> ilog2_pow2(tpc), col0 = (tile & (tpc - 1)) * CT;
+        const int be = window_begin(p, c), en = be + p.in_T;
+        const float4* src = reinterpret_cast<const float4*>(p.in + (size_t)c * p.in_T * NN + col0);
+        float4* xs4 = reinterpret_cast<float4*>(smem);
+        const int t0 = tid / V4;
+        ptrdiff_t off = (ptrdiff_t)(t0 - be) * (NN / 4) + tid % V4;
+        const ptrdiff_t off_step = (ptrdiff_t)kRowStep * (NN / 4);
+        LCT_UNROLL
+        for (int u = 0; u < kIters; ++u, off += off_step) {
+            const int i = tid + u * kThreads, t = t0 + u * kRowStep;
+            const bool ok = t >= be && t < en;
+            if (i < kSlots) cp_async16(xs4 + i, ok ? src + off : src, ok);
+        }
+        cp_async_commit();
+    }
+
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem_base, int tid, int bx, int by, int it) {
+        unsigned char* smem = smem_base + TwS::kBytes;
+        const int col = tid % CT, tau = line_thread<CT>(tid);
+        const int NN = p.N * p.N, tpc = NN / CT;
+        const TileWalk walk(p, tpc, kPersist);
+        int tile, col0, c;
+        if constexpr (kPersist) {
+            tile = bx + it * walk.G;
+            if (tile >= walk.total) return;                  // block-uniform: the barriers are in the driver
+            col0 = (tile & (tpc - 1)) * CT;
+            c = tile >> ilog2_pow2(tpc);
+        } else {
+            tile = by * tpc + bx; col0 = bx * CT; c = by;
+        }
+        float* xs = reinterpret_cast<float*>(smem);
+        float2* zs = reinterpret_cast<float2*>(smem + kXs);
+        if constexpr (PH == 0 && kPersist) {
+            if (it == 0) {
+                for (int j = tid; j < M; j += kThreads) reinterpret_cast<float4*>(smem + kWork)[j] = LCT_LDG(p.ell + j);
+                issue_tile(p, smem, tid, tile);
+            }
+            cp_async_wait_all();                             // later tiles were issued during the previous tile's stages
+        } else if constexpr (PH == 0) {
+            // one tile per block: plain 128-bit loads through registers, same slot walk as issue_tile
+            const int be = window_begin(p, c), en = be + p.in_T;
+            constexpr int V4 = CT / 4, kSlots = (M + 2) * V4;
+            const float4* src = reinterpret_cast<const float4*>(p.in + (size_t)c * p.in_T * NN + col0);
+            float4* xs4 = reinterpret_cast<float4*>(smem);
+            for (int j = tid; j < M; j += kThreads) reinterpret_cast<float4*>(smem + kWork)[j] = LCT_LDG(p.ell + j);
+            constexpr int kRowStep = kThreads / V4, kIters = (kSlots + kThreads - 1) / kThreads;
+            const int t0 = tid / V4;
+            ptrdiff_t off = (ptrdiff_t)(t0 - be) * (NN / 4) + tid % V4;
+            const ptrdiff_t off_step = (ptrdiff_t)kRowStep * (NN / 4);
+            float4 v[kIters];
+            LCT_UNROLL
+            for (int u = 0; u < kIters; ++u, off += off_step) {
+                const int t = t0 + u * kRowStep;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t >= be && t < en) v[u] = LCT_LDG(src + off);
+            }
+            if (p.ahead > 0 && tile + p.ahead < walk.total) {
+                // own loads are in flight: ask L2 for the tile of the block that will run here about one block life later
+                const int nt = tile + p.ahead;
+                const float* ns = p.in + (size_t)(nt >> ilog2_pow2(tpc)) * p.in_T * NN + (size_t)(nt & (tpc - 1)) * CT;     // one 128-byte line per time bin
+                for (int t = tid; t < p.in_T; t += kThreads) prefetch_l2(ns + (size_t)t * NN);
+            }
+            LCT_UNROLL
+            for (int u = 0; u < kIters; ++u) {
+                const int i = tid + u * kThreads;
+                if (i < kSlots) xs4[i] = v[u];
+            }
+        } else if constexpr (PH == 1) {
+            fwd_stage<P, 0, true, TwS>(tau,
+                [&](int pos, int slot) {
+                    // rows longer than three taps sit below kTailRows = 2 * st(0): first input of a butterfly only
+                    const float4* ell = reinterpret_cast<const float4*>(smem + kWork);
+                    if (slot % P::radix(0) == 0)
+                        return make_float2(band_dot<true>(p, ell, 2 * pos, xs + col), band_dot<true>(p, ell, 2 * pos + 1, xs + col));
+                    return make_float2(band_dot<false>(p, ell, 2 * pos, xs + col), band_dot<false>(p, ell, 2 * pos + 1, xs + col));
+                },
+                [&](int pos, int, float2 v) { zs[pos * CT + col] = v; });
+        } else if constexpr (PH < 1 + P::S) {
+            constexpr int s = PH - 1;
+            if constexpr (s == 1 && kPersist) {              // xs was consumed by the gather: start the next tile's copy
+                if (tile + walk.G < walk.total) issue_tile(p, smem, tid, tile + walk.G);
+            }
+            fwd_stage<P, s, false, TwS>(tau,
+                [&](int pos, int) { return zs[pos * CT + col]; },
+                [&](int pos, int, float2 v) { zs[pos * CT + col] = v; });
+        } else {
+            // X[k] = Ev + w^k Od and X[M-k] = conj(Ev - w^k Od) from the pair (Z[k], Z[M-k])
+            float2* dst = p.s1 + (size_t)c * (M + 1) * NN + col0 + col;
+            const float2* zc = zs + col;
+            auto emit = [&](int k, int pos_k, int pos_mk, float2* lo, float2* hi) {
+                const float2 zk = zc[pos_k * CT];
+                const float2 zm = cconj(zc[pos_mk * CT]);
+                const float2 ev = cscale(cadd(zk, zm), 0.5f);
+                const float2 d = csub(zk, zm);
+                const float2 od = make_float2(0.5f * d.y, -0.5f * d.x);
+                const float2 t = TwS::mul(od, k * (kTwN / (2 * M)));
+                *lo = cadd(ev, t);
+                if (hi != lo) *hi = cconj(csub(ev, t));       // (a compile-time flag instead of the compare: 6 % slower at M = 128)
+            };
+            constexpr int kPairs = (M / 2) / P::TL, kBlocks = M / P::TL;        // k = tau + m*TL < M/2
+            float2* lo = dst + (size_t)tau * NN;
+            float2* hi = dst + (size_t)(M - tau) * NN;
+            const size_t step = (size_t)P::TL * NN;
+            const int pos_tau = P::freq_to_pos(tau);
+            // position of frequency M - k: for tau > 0, M - k = (kBlocks - 1 - m) TL + (TL - tau), two disjoint
+            // bit fields of the digit reversal (a bit permutation); for tau == 0 it is (kBlocks - m) TL mod M
+            const int pos_neg = P::freq_to_pos((P::TL - tau) & (P::TL - 1));
+            LCT_UNROLL
+            for (int m = 0; m < kPairs; ++m) {
+                const int pos_mk = tau != 0 ? pos_neg + P::freq_to_pos((kBlocks - 1 - m) * P::TL)
+                                            : P::freq_to_pos(((kBlocks - m) * P::TL) & (M - 1));
+                emit(tau + m * P::TL, pos_tau + P::freq_to_pos(m * P::TL), pos_mk, lo, hi);   // disjoint bit fields
+                lo += step;
+                hi -= step;
+            }
+            if (tau == 0) emit(M / 2, P::freq_to_pos(M / 2), P::freq_to_pos(M / 2), dst + (size_t)(M / 2) * NN, dst + (size_t)(M / 2) * NN);
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------
 // K5: Hermitian inverse FFT along T (keep t < M), real part, mtxi gather.
 // ---------------------------------------------------------------------------
@@ -377,48 +577,45 @@ template <class P, int CT_> struct TimeInv {
     // 1024 threads/SM at <= 64 regs; the 32-wide butterflies need 128 regs (512 threads/SM)
     static constexpr int kMinBlocks = (P::E >= 32) ? (512 / kThreads > 0 ? 512 / kThreads : 1) : ((kThreads >= 1024) ? 1 : 1024 / kThreads);
     struct Regs { float2 a[P::E]; };
-    static void grid(const Params& p, int& gx, int& gy) { gx = p.N * p.N / CT; gy = p.C; }
-    static int iterations(const Params&) { return 1; }
+    static void grid(const Params& p, int& gx, int& gy) { gx = TileWalk(p, p.N * p.N / CT).G; gy = 1; }
+    static int iterations(const Params& p) { return TileWalk(p, p.N * p.N / CT).iterations(); }
 
     static constexpr bool kHasPrologue = true;
     static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwS::fill(smem, tid, kThreads); }
 
-    template <int PH> static LCT_DEV void phase(const Params& p, Regs& r, unsigned char* smem_base, int tid, int bx, int by, int) {
+    // spectrum tile -> zs[(M+1)][CT] c64 by 16-byte asynchronous copies (two columns each)
+    static LCT_DEV void issue_tile(const Params& p, unsigned char* smem, int tid, int tile) {
+        constexpr int V2 = CT / 2, kSlots = (M + 1) * V2;
+        static_assert(kThreads % V2 == 0, "column pair must be fixed per thread");
+        constexpr int kIters = (kSlots + kThreads - 1) / kThreads;
+        const int NN = p.N * p.N, tpc = NN / CT, c = tile >> ilog2_pow2(tpc), col0 = (tile & (tpc - 1)) * CT;
+        const float4* src = reinterpret_cast<const float4*>(p.s1 + (size_t)c * (M + 1) * NN + col0);
+        float4* zs4 = reinterpret_cast<float4*>(smem);
+        size_t off = (size_t)(tid / V2) * (NN / 2) + tid % V2;           // stepped per slot, not recomputed
+        const size_t off_step = (size_t)(kThreads / V2) * (NN / 2);
+        LCT_UNROLL
+        for (int u = 0; u < kIters; ++u, off += off_step)
+            if (tid + u * kThreads < kSlots) cp_async16(zs4 + tid + u * kThreads, src + off, true);
+        cp_async_commit();
+    }
+
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs& r, unsigned char* smem_base, int tid, int bx, int, int it) {
         unsigned char* smem = smem_base + TwS::kBytes;
         const int col = tid % CT, tau = line_thread<CT>(tid);
-        const int NN = p.N * p.N, col0 = bx * CT, c = by;
+        const int NN = p.N * p.N, tpc = NN / CT;
+        const TileWalk walk(p, tpc);
+        const int tile = bx + it * walk.G;
+        if (tile >= walk.total) return;                      // block-uniform: the barriers are in the driver
+        const int col0 = (tile & (tpc - 1)) * CT, c = tile >> ilog2_pow2(tpc);
         float2* zs = reinterpret_cast<float2*>(smem);
         float* vol = reinterpret_cast<float*>(smem + kZs);
         constexpr int SL = P::S - 1;
         if constexpr (PH == 0) {
-            // spectrum tile -> zs[(M+1)][CT] c64 (128-bit loads: two columns per lane)
-            constexpr int V2 = CT / 2, kSlots = (M + 1) * V2;
-            const float4* src = reinterpret_cast<const float4*>(p.s1 + (size_t)c * (M + 1) * NN + col0);
-            float4* zs4 = reinterpret_cast<float4*>(smem);
-            for (int j = tid; j < M; j += kThreads) reinterpret_cast<float4*>(smem + kWork)[j] = LCT_LDG(p.ell + j);
-            static_assert(kThreads % V2 == 0, "column pair must be fixed per thread");
-            constexpr int kIters = (kSlots + kThreads - 1) / kThreads;
-            size_t off = (size_t)(tid / V2) * (NN / 2) + tid % V2;           // stepped per slot, not recomputed
-            const size_t off_step = (size_t)(kThreads / V2) * (NN / 2);
-            float4 v[kIters];
-            LCT_UNROLL
-            for (int u = 0; u < kIters; ++u, off += off_step)
-                if (tid + u * kThreads < kSlots) v[u] = src[off];
-            if (p.ahead > 0) {
-                const int gx = NN / CT;
-                const long long next = (long long)by * gx + bx + p.ahead;
-                const int nc = (int)(next / gx), nb = (int)(next % gx);
-                if (nc < p.C) {
-                    const char* ns = reinterpret_cast<const char*>(p.s1 + (size_t)nc * (M + 1) * NN + (size_t)nb * CT);
-                    for (int i = tid; i < 2 * (M + 1); i += kThreads)                       // two 128-byte lines per frequency
-                        prefetch_l2(ns + (size_t)(i >> 1) * NN * sizeof(float2) + (i & 1) * 128);
-                }
+            if (it == 0) {
+                for (int j = tid; j < M; j += kThreads) reinterpret_cast<float4*>(smem + kWork)[j] = LCT_LDG(p.ell + j);
+                issue_tile(p, smem, tid, tile);
             }
-            LCT_UNROLL
-            for (int u = 0; u < kIters; ++u) {
-                const int i = tid + u * kThreads;
-                if (i < kSlots) zs4[i] = v[u];
-            }
+            cp_async_wait_all();                             // later tiles were issued during the previous tile's gather
         } else if constexpr (PH == 1) {
             // Z[k] = (X[k] + conj X[M-k]) + i conj(w^k) (X[k] - conj X[M-k])
             auto z_at = [&](int k) -> float2 {
@@ -452,6 +649,8 @@ template <class P, int CT_> struct TimeInv {
                 [&](int pos, int, float2 v) { vol[(2 * pos) * CT + col] = v.x; vol[(2 * pos + 1) * CT + col] = v.y; });
             if (tau == 0) { vol[M * CT + col] = 0.f; vol[(M + 1) * CT + col] = 0.f; }   // pad rows for band_dot
         } else if constexpr (PH == kPhases - 1) {
+            // zs was consumed by the last stage: the next tile's spectrum flies in while this one is gathered
+            if (SL > 0 && tile + walk.G < walk.total) issue_tile(p, smem, tid, tile + walk.G);
             const int be = window_begin(p, c);
             float* dst = p.out + (size_t)c * p.out_T * NN + col0 + col;
             float* d = dst + (size_t)tau * NN;

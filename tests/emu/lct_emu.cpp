@@ -33,7 +33,9 @@ template <class K, int PH> struct EmuPhases {
 
 struct EmuLauncher {
     void mark(int) {}
-    template <class K> int launch(const lct::Params& p) {
+    template <class K> int launch(const lct::Params& p0) {
+        lct::Params p = p0;
+        p.ahead = 3;                                         // three "resident" blocks: persistent kernels walk several tiles each
         int gx, gy;
         K::grid(p, gx, gy);
         const int iters = K::iterations(p);
