@@ -81,7 +81,14 @@ template <int N, class Launcher> int launch_row_inv(const Params& p, Launcher& l
     return l.template launch<RowInv<typename RowInvPlan<2 * N>::type, RowTile<N>::CT>>(p);
 }
 template <int N, class Launcher> int launch_col_filter(const Params& p, Launcher& l) {
-    return l.template launch<ColFilter<typename LinePlan<2 * N>::type, LineRows<N>::RB>>(p);
+    // 512-point lines: two 256-point transforms by output parity (16-wide butterflies): 564 vs 682 us at cfg5, 5 % ahead
+    // with four channels.  At N = 128 the register-cached filter of ColFilter wins clearly (288 vs 460 us at cfg4).
+    if constexpr (N >= 256) {
+        using PL = typename LinePlan<N>::type;
+        return l.template launch<ColFilterSplit<PL, 256 / PL::TL>>(p);
+    }
+    else
+        return l.template launch<ColFilter<typename LinePlan<2 * N>::type, LineRows<N>::RB>>(p);
 }
 template <int N, class Launcher> int launch_plane(const Params& p, Launcher& l) {
     if constexpr (plane_fusable(N)) return l.template launch<typename PlaneKernel<N>::type>(p);

@@ -879,6 +879,102 @@ template <class P, int RB_> struct ColFilter {
 };
 
 // ---------------------------------------------------------------------------
+// K3 for long lines (N = 256): the same pass with the zero-extended 2N-point transform written as two
+// N-point transforms -- even output frequencies FFT_N(x), odd ones FFT_N(x w_2N^n) -- each filtered and
+// inverted, y[n] = y_even[n] + conj(w_2N^n) y_odd[n].  Same arithmetic as ColFilter, but the butterflies
+// are 16 wide instead of 32: a third of the registers and twice the resident warps.  P is the N-point plan.
+// ---------------------------------------------------------------------------
+template <class P, int RB_> struct ColFilterSplit {
+    static_assert(P::S == 2, "ColFilterSplit needs a two-stage plan");
+    static_assert(32 % P::TL == 0, "the threads of one line must share a warp");
+    static constexpr int N = P::L, L = 2 * N, RB = RB_, kThreads = P::TL * RB;
+    static constexpr int kPhases = 3;
+    using TwL = TwLine<P>;
+    static constexpr bool kWarpSync = true;
+    static constexpr int kMinBlocks = 2;
+    static constexpr int PAD = 1;
+    static constexpr int RS = N + P::R0 * PAD + ((P::TL < 16) ? 8 : 0);    // row stride in float2
+    static constexpr size_t kSmem = TwL::kBytes + (size_t)2 * RB * RS * sizeof(float2);     // even and odd exchange rows
+    struct Regs { float2 in[P::E]; };
+    static void grid(const Params& p, int& gx, int& gy) { gx = L / RB; gy = p.M + 1; }
+    static int iterations(const Params& p) { return p.C; }
+    static LCT_DEV int padpos(int pos) { return pos + (pos / P::st(0)) * PAD; }
+
+    static LCT_DEV void fetch(const float2* row, int tau, Regs& r) {
+        for_each_slot<P, 0>(tau, [&](int pos, int slot) { r.in[slot] = row[pos]; });
+    }
+
+    static constexpr bool kHasPrologue = true;
+    static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwL::fill(smem, tid, kThreads); }
+
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs& r, unsigned char* smem, int tid, int bx, int by, int it) {
+        const int tau = tid % P::TL, rl = tid / P::TL;
+        const int kh = bx * RB + rl, kt = by, c = it;
+        float2* ze = reinterpret_cast<float2*>(smem + TwL::kBytes) + rl * RS;
+        float2* zo = ze + RB * RS;
+        const size_t chan = (size_t)(p.M + 1) * L * N;
+        float2* row = p.s2 + (size_t)c * chan + ((size_t)kt * L + kh) * N;
+        if constexpr (PH == 0) {
+            if (it == 0 && p.ahead > 0) {
+                // warm L2 with channel 0's rows and the filter rows of the block one residency ahead
+                const int gx = L / RB;
+                const long long next = (long long)by * gx + bx + p.ahead;
+                if (next / gx <= p.M) {
+                    const size_t first = (size_t)(next / gx) * L + (size_t)(next % gx) * RB;          // kt * L + kh
+                    const char* rows = reinterpret_cast<const char*>(p.s2 + first * N);
+                    const char* filt = reinterpret_cast<const char*>(p.filt + first * L);
+                    constexpr int kRowLines = RB * N * (int)sizeof(float2) / 128, kFiltLines = RB * L * (int)sizeof(float2) / 128;
+                    for (int i = tid; i < kRowLines; i += kThreads) prefetch_l2(rows + (size_t)i * 128);
+                    for (int i = tid; i < kFiltLines; i += kThreads) prefetch_l2(filt + (size_t)i * 128);
+                }
+            }
+            if (it == 0) fetch(row, tau, r);
+            fwd_stage<P, 0, false, TwL>(tau,
+                [&](int, int slot) { return r.in[slot]; },
+                [&](int pos, int, float2 v) { ze[padpos(pos)] = v; });
+            fwd_stage<P, 0, false, TwL>(tau,
+                [&](int pos, int slot) { return TwGlobal::mul(r.in[slot], pos * (kTwN / L)); },
+                [&](int pos, int, float2 v) { zo[padpos(pos)] = v; });
+            if (it + 1 < p.C) fetch(row + chan, tau, r);        // next channel's row flies during this one's math
+        } else if constexpr (PH == 1) {
+            // natural filter layout [kt][kh][kw]: even parity reads kw = 2f, odd parity kw = 2f + 1
+            const float2* f = p.filt + ((size_t)kt * L + kh) * L;
+            float2 w[P::E], a[P::E];
+            for_each_slot<P, 1>(tau, [&](int pos, int slot) {
+                float2 v = LCT_LDG(f + 2 * P::template freq_of<1>(pos, slot));
+                if (p.conj_filter) v.y = -v.y;
+                w[slot] = v;
+            });
+            fwd_stage<P, 1, false, TwL>(tau,
+                [&](int pos, int) { return ze[padpos(pos)]; },
+                [&](int, int slot, float2 v) { a[slot] = cmul(v, w[slot]); });
+            inv_stage<P, 1, false, TwL>(tau,
+                [&](int, int slot) { return a[slot]; },
+                [&](int pos, int, float2 v) { ze[padpos(pos)] = v; });
+            for_each_slot<P, 1>(tau, [&](int pos, int slot) {
+                float2 v = LCT_LDG(f + 2 * P::template freq_of<1>(pos, slot) + 1);
+                if (p.conj_filter) v.y = -v.y;
+                w[slot] = v;
+            });
+            fwd_stage<P, 1, false, TwL>(tau,
+                [&](int pos, int) { return zo[padpos(pos)]; },
+                [&](int, int slot, float2 v) { a[slot] = cmul(v, w[slot]); });
+            inv_stage<P, 1, false, TwL>(tau,
+                [&](int, int slot) { return a[slot]; },
+                [&](int pos, int, float2 v) { zo[padpos(pos)] = v; });
+        } else {
+            float2 ya[P::E];
+            inv_stage<P, 0, false, TwL>(tau,
+                [&](int pos, int) { return ze[padpos(pos)]; },
+                [&](int, int slot, float2 v) { ya[slot] = v; });
+            inv_stage<P, 0, false, TwL>(tau,
+                [&](int pos, int) { return zo[padpos(pos)]; },
+                [&](int pos, int slot, float2 v) { row[pos] = cadd(ya[slot], TwGlobal::mulc(v, pos * (kTwN / L))); });
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
 // Plane-resident fusion of K2 + K3 + K4 (N <= 64): one block owns one (c, kt) plane.
 // The zero-extended 2N x N half-transformed plane lives in shared memory (row stride N+1
 // float2, conflict-free for lanes along W and for lanes along H), so the plane is read
