@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kSkipThreads, 2) skip_kernel(SkipParams p) {
 // once per thread row (3 x (LDS.128 + 2 LDS.32)) into the rotating register window.
 // Used whenever the window source is a single channel (always, except the data gradient at D > 1).
 // ---------------------------------------------------------------------------------------------
-constexpr int kSkipRing = 8;
+constexpr int kSkipRing = 8;               // a power of two (ring slots are masked, not divided)
 
 __device__ __forceinline__ void skip_cp_async16(float* dst_smem, const float* src, bool valid) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(kSkipThreads, 2) skip_ring_kernel(SkipParams p
     const bool stage_ctr = MODE == kSkipForward || (MODE == kSkipWeightGrad && p.D == 1);
     const float* ctr_src = (MODE == kSkipDataGrad) ? nullptr : p.add + (size_t)b * p.D * vol;
     float* cring = ring + kSkipRing * plane;
+    float* out_b = p.out + (size_t)b * ((MODE == kSkipDataGrad) ? 1 : p.D) * vol;      // unused by the weight gradient
     const int cplane = RB * p.N;
 
     float w[27];
@@ -233,24 +234,45 @@ __global__ void __launch_bounds__(kSkipThreads, 2) skip_ring_kernel(SkipParams p
     for (int i = tid; i < kSkipRing * plane / 4; i += kSkipThreads) reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
-    auto slot_of = [&](int u) { return ring + ((u + 1) % kSkipRing) * plane; };          // u >= -1
+    // Everything that does not change from plane to plane is worked out once: this thread's (at most two) copy
+    // slots of a window plane as {shared offset, offset inside a global plane, row inside the volume}, its centre
+    // slot, and its three window rows.  Per plane only the ring slot and the plane base are added.
+    const int NN = p.N * p.N;
+    int cs_off[2], cg_off[2];
+    bool cs_has[2], cs_row_ok[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int i = tid + k * kSkipThreads;
+        const int r = i / XQ, q = i - r * XQ, yy = y0 - 1 + r;
+        cs_has[k] = i < (RB + 2) * XQ;
+        cs_row_ok[k] = cs_has[k] && yy >= 0 && yy < p.N;
+        cs_off[k] = r * RS + 4 + 4 * q;
+        cg_off[k] = yy * p.N + 4 * q;
+    }
+    const int my_ctr = yl * p.N + x0;              // centre slot inside a centre plane
+    const int my_row = yl * RS + 4 + x0;           // first of this thread's three window rows inside a window plane
+    const int my_at = y * p.N + x0;                // this thread's four outputs inside a global plane
+
+    auto ring_slot = [&](int u) { return (u + 1) & (kSkipRing - 1); };                  // u >= -1; kSkipRing is a power of two
     auto issue = [&](int u) {                                                           // plane u -> its slot, one group
-        float* dst = slot_of(u);
+        const int slot = ring_slot(u);
+        float* dst = ring + slot * plane;
         const bool t_ok = u >= 0 && u < p.T && u <= t1;
-        for (int i = tid; i < (RB + 2) * XQ; i += kSkipThreads) {
-            const int r = i / XQ, q = i % XQ, yy = y0 - 1 + r;
-            const bool ok = t_ok && yy >= 0 && yy < p.N;
-            skip_cp_async16(dst + r * RS + 4 + 4 * q, ok ? src + ((size_t)u * p.N + yy) * p.N + 4 * q : src, ok);
-        }
+        const float* gp = src + (size_t)(t_ok ? u : 0) * NN;
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (cs_has[k]) {
+                const bool ok = t_ok && cs_row_ok[k];
+                skip_cp_async16(dst + cs_off[k], ok ? gp + cg_off[k] : src, ok);
+            }
         if (MODE != kSkipDataGrad && stage_ctr && active) {
             const bool ok = u >= t0 && u < t1;
-            skip_cp_async16(cring + ((u + 1) % kSkipRing) * cplane + yl * p.N + x0,
-                            ok ? ctr_src + ((size_t)u * p.N + y) * p.N + x0 : ctr_src, ok);
+            skip_cp_async16(cring + slot * cplane + my_ctr, ok ? ctr_src + (size_t)u * NN + my_at : ctr_src, ok);
         }
         skip_cp_commit();
     };
     auto fetch = [&](int u, float (&pl)[3][6]) {                                        // this thread's rows of plane u
-        const float* base = slot_of(u) + yl * RS + 4 + x0;
+        const float* base = ring + ring_slot(u) * plane + my_row;
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
             const float* r = base + dy * RS;
@@ -268,11 +290,11 @@ __global__ void __launch_bounds__(kSkipThreads, 2) skip_ring_kernel(SkipParams p
 
     auto step = [&](int t, float (&lo)[3][6], float (&mid)[3][6], float (&hi)[3][6]) {
         const bool live = active && t < t1;
-        const size_t at = ((size_t)t * p.N + y) * p.N + x0;
+        const size_t at = (size_t)t * NN + my_at;
         float4 ctr = make_float4(0.f, 0.f, 0.f, 0.f);
         if (MODE != kSkipDataGrad && live) {
             if (stage_ctr) {
-                ctr = *reinterpret_cast<const float4*>(cring + ((t + 1) % kSkipRing) * cplane + yl * p.N + x0);
+                ctr = *reinterpret_cast<const float4*>(cring + ring_slot(t) * cplane + my_ctr);
             } else {
                 const float* cp = ctr_src + at;
                 for (int d = 0; d < p.D; ++d, cp += vol) {
@@ -305,8 +327,8 @@ __global__ void __launch_bounds__(kSkipThreads, 2) skip_ring_kernel(SkipParams p
                         s[j] = fmaf(w[2 * 9 + dy * 3 + dx], hi[dy][dx + j], s[j]);
                     }
             if (MODE == kSkipForward) {
-                const float* ap = p.add + (size_t)b * p.D * vol + at;
-                float* op = p.out + (size_t)b * p.D * vol + at;
+                const float* ap = ctr_src + at;
+                float* op = out_b + at;
                 *reinterpret_cast<float4*>(op) = make_float4(ctr.x + s[0], ctr.y + s[1], ctr.z + s[2], ctr.w + s[3]);
                 for (int d = 1; d < p.D; ++d) {
                     ap += vol; op += vol;
@@ -314,7 +336,7 @@ __global__ void __launch_bounds__(kSkipThreads, 2) skip_ring_kernel(SkipParams p
                     *reinterpret_cast<float4*>(op) = make_float4(a.x + s[0], a.y + s[1], a.z + s[2], a.w + s[3]);
                 }
             } else {
-                *reinterpret_cast<float4*>(p.out + (size_t)b * vol + at) = make_float4(s[0], s[1], s[2], s[3]);
+                *reinterpret_cast<float4*>(out_b + at) = make_float4(s[0], s[1], s[2], s[3]);
             }
         }
         skip_cp_wait<kSkipRing - 3>();             // plane t + 2 has landed (this thread's copies) ...
