@@ -74,11 +74,21 @@ template <int M, class Launcher> int launch_time_fwd(const Params& p, Launcher& 
 template <int M, class Launcher> int launch_time_inv(const Params& p, Launcher& l) {
     return l.template launch<TimeInv<typename TimeInvPlan<M>::type, TimeTile<M>::CT>>(p);
 }
+// 512-point columns (N = 256) run as two 256-point transforms by parity (RowFwdSplit / RowInvSplit)
+#ifndef LCT_ROW_SPLIT
+#define LCT_ROW_SPLIT 1
+#endif
 template <int N, class Launcher> int launch_row_fwd(const Params& p, Launcher& l) {
-    return l.template launch<RowFwd<typename RowFwdPlan<2 * N>::type, RowTile<N>::CT>>(p);
+    if constexpr (N >= 256 && LCT_ROW_SPLIT)
+        return l.template launch<RowFwdSplit<typename ColPlan<N>::type, 16>>(p);
+    else
+        return l.template launch<RowFwd<typename RowFwdPlan<2 * N>::type, RowTile<N>::CT>>(p);
 }
 template <int N, class Launcher> int launch_row_inv(const Params& p, Launcher& l) {
-    return l.template launch<RowInv<typename RowInvPlan<2 * N>::type, RowTile<N>::CT>>(p);
+    if constexpr (N >= 256 && LCT_ROW_SPLIT)
+        return l.template launch<RowInvSplit<typename ColPlan<N>::type, 16>>(p);
+    else
+        return l.template launch<RowInv<typename RowInvPlan<2 * N>::type, RowTile<N>::CT>>(p);
 }
 template <int N, class Launcher> int launch_col_filter(const Params& p, Launcher& l) {
     // 512-point lines: two 256-point transforms by output parity (16-wide butterflies): 564 vs 682 us at cfg5, 5 % ahead

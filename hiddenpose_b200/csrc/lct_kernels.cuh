@@ -789,6 +789,121 @@ template <class P, int CT_> struct RowInv {
 };
 
 // ---------------------------------------------------------------------------
+// K2 / K4 for long columns (N = 256): the zero-extended 2N-point transform along H written as two N-point
+// transforms by output parity -- even rows FFT_N(x), odd rows FFT_N(x w_2N^n); on the way back
+// y[n] = IFFT_N(X_even)[n] + conj(w_2N^n) IFFT_N(X_odd)[n].  The two parities run side by side: threads
+// [0, TL*CT) own the even rows, threads [TL*CT, 2*TL*CT) the odd rows, each half with its own exchange buffer
+// (the inverse adds the halves in a third phase).  16-wide butterflies at 64 registers and two 512-thread blocks
+// per SM instead of 32-wide ones at 128 registers: cfg5 K2 240 -> 184 us, K4 225 -> 196 us.  (Running the parities
+// one after the other through one buffer measured 196 us forward and, with the even half parked in the output
+// rows, 251 us inverse.)  P is the N-point plan; S2 rows stay in natural kh order, so K3 is unchanged.
+// ---------------------------------------------------------------------------
+template <class P, int CT_> struct RowFwdSplit {
+    static_assert(P::S == 2, "RowFwdSplit needs a two-stage plan");
+    using TwS = TwNone;
+    static constexpr int N = P::L, L = 2 * N, CT = CT_, kHalf = P::TL * CT, kThreads = 2 * kHalf;
+    static constexpr int kPhases = 2;
+    static constexpr bool kWarpSync = false;
+    static constexpr int kMinBlocks = (kThreads >= 1024) ? 1 : 1024 / kThreads;      // <= 64 regs
+    static constexpr size_t kSmem = TwS::kBytes + (size_t)2 * N * CT * sizeof(float2);
+    static_assert(kHalf % 32 == 0, "a warp must not straddle the two parities");
+    struct Regs {};
+    static void grid(const Params& p, int& gx, int& gy) { gx = p.N / CT; gy = p.C * (p.M + 1); }
+    static int iterations(const Params&) { return 1; }
+
+    static constexpr bool kHasPrologue = true;
+    static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwS::fill(smem, tid, kThreads); }
+
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem_base, int tid, int bx, int by, int) {
+        unsigned char* smem = smem_base + TwS::kBytes;
+        const int parity = tid / kHalf, t = tid % kHalf;
+        const int col = t % CT, tau = line_thread<CT>(t);
+        float2* z = reinterpret_cast<float2*>(smem) + parity * (N * CT);
+        auto st_s = [&](int pos, int, float2 v) { z[pos * CT + col] = v; };
+        if constexpr (PH == 0) {
+            const float2* src = p.s1 + (size_t)by * N * N + bx * CT + col;
+            if (p.ahead > 0) {
+                const int gx = N / CT;
+                const long long next = (long long)by * gx + bx + p.ahead;
+                if (next / gx < (long long)p.C * (p.M + 1)) {
+                    const char* ns = reinterpret_cast<const char*>(p.s1 + (size_t)(next / gx) * N * N + (size_t)(next % gx) * CT);
+                    constexpr int kLines = (CT * (int)sizeof(float2) + 127) / 128;
+                    for (int i = tid; i < N * kLines; i += kThreads)
+                        prefetch_l2(ns + (size_t)(i / kLines) * N * sizeof(float2) + (i % kLines) * 128);
+                }
+            }
+            if (parity == 0)
+                fwd_stage<P, 0, false, TwS>(tau, [&](int pos, int) { return src[(size_t)pos * N]; }, st_s);
+            else
+                fwd_stage<P, 0, false, TwS>(tau,
+                    [&](int pos, int) { return TwGlobal::mul(src[(size_t)pos * N], pos * (kTwN / L)); }, st_s);
+        } else {
+            float2* dst = p.s2 + (size_t)by * L * N + bx * CT + col + (size_t)parity * N;
+            fwd_stage<P, 1, false, TwS>(tau,
+                [&](int pos, int) { return z[pos * CT + col]; },
+                [&](int pos, int slot, float2 v) { dst[(size_t)P::template freq_of<1>(pos, slot) * (2 * N)] = v; });
+        }
+    }
+};
+
+template <class P, int CT_> struct RowInvSplit {
+    static_assert(P::S == 2, "RowInvSplit needs a two-stage plan");
+    using TwS = TwNone;
+    static constexpr int N = P::L, L = 2 * N, CT = CT_, kHalf = P::TL * CT, kThreads = 2 * kHalf;
+    static constexpr int kPhases = 3;
+    static constexpr bool kWarpSync = false;
+    static constexpr int kMinBlocks = (kThreads >= 1024) ? 1 : 1024 / kThreads;      // <= 64 regs
+    static constexpr size_t kSmem = TwS::kBytes + (size_t)2 * N * CT * sizeof(float2);
+    static_assert(kHalf % 32 == 0, "a warp must not straddle the two parities");
+    struct Regs {};
+    static void grid(const Params& p, int& gx, int& gy) { gx = p.N / CT; gy = p.C * (p.M + 1); }
+    static int iterations(const Params&) { return 1; }
+
+    static constexpr bool kHasPrologue = true;
+    static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwS::fill(smem, tid, kThreads); }
+
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem_base, int tid, int bx, int by, int) {
+        unsigned char* smem = smem_base + TwS::kBytes;
+        float2* zs = reinterpret_cast<float2*>(smem);
+        if constexpr (PH < 2) {
+            const int parity = tid / kHalf, t = tid % kHalf;
+            const int col = t % CT, tau = line_thread<CT>(t);
+            float2* z = zs + parity * (N * CT);
+            auto ld_s = [&](int pos, int) { return z[pos * CT + col]; };
+            auto st_s = [&](int pos, int, float2 v) { z[pos * CT + col] = v; };
+            if constexpr (PH == 0) {
+                const float2* src = p.s2 + (size_t)by * L * N + bx * CT + col + (size_t)parity * N;
+                if (p.ahead > 0) {
+                    const int gx = N / CT;
+                    const long long next = (long long)by * gx + bx + p.ahead;
+                    if (next / gx < (long long)p.C * (p.M + 1)) {
+                        const char* ns = reinterpret_cast<const char*>(p.s2 + (size_t)(next / gx) * L * N + (size_t)(next % gx) * CT);
+                        constexpr int kLines = (CT * (int)sizeof(float2) + 127) / 128;
+                        for (int i = tid; i < L * kLines; i += kThreads)
+                            prefetch_l2(ns + (size_t)(i / kLines) * N * sizeof(float2) + (i % kLines) * 128);
+                    }
+                }
+                inv_stage<P, 1, false, TwS>(tau,
+                    [&](int pos, int slot) { return src[(size_t)P::template freq_of<1>(pos, slot) * (2 * N)]; }, st_s);
+            } else {
+                inv_stage<P, 0, false, TwS>(tau, ld_s, st_s);       // in place: a butterfly writes the positions it read
+            }
+        } else {
+            // y[n] = y_even[n] + conj(w_2N^n) y_odd[n]
+            float2* dst = p.s1 + (size_t)by * N * N + bx * CT;
+            const float2* zo = zs + N * CT;
+            constexpr int kIters = N * CT / kThreads;
+            static_assert(N * CT % kThreads == 0 && kThreads % CT == 0, "the plane tile must divide among the threads");
+            LCT_UNROLL
+            for (int u = 0; u < kIters; ++u) {
+                const int i = tid + u * kThreads, n = i / CT, col = i % CT;
+                dst[(size_t)n * N + col] = cadd(zs[i], TwGlobal::mulc(zo[i], n * (kTwN / L)));
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
 // K3: along W (the contiguous axis): zero-extended FFT, filter multiply, inverse
 // FFT, crop -- in place on S2.  One block = RB consecutive kh rows of one kt
 // plane; it loops over the channels so the filter row stays in registers.

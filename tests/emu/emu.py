@@ -18,7 +18,7 @@ def build(force=False):
     if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(s) for s in srcs):
         return SO
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-I" + CSRC, "-I" + cuda_inc,
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC"] + os.environ.get("LCT_EMU_DEFS", "").split() + ["-shared", "-I" + CSRC, "-I" + cuda_inc,
                            "-o", SO, os.path.join(HERE, "lct_emu.cpp")])
     return SO
 

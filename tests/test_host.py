@@ -143,6 +143,26 @@ def test_emulated_kernels_have_no_intra_phase_races():
     assert O.rel_l2(a, yo) <= 1e-5
 
 
+def test_emulated_parity_split_row_kernels():
+    """N = 256 runs the H-axis passes as two 256-point transforms by output parity (RowFwdSplit / RowInvSplit):
+    each stage alone against numpy's FFT, and bit-identical with the threads of every phase run backwards."""
+    from tests.emu.emu import EmuPlan
+    N, M = 256, 32
+    plan = EmuPlan(N, M, 0.16)
+    rs = np.random.RandomState(7)
+    x = np.zeros((1, M, N, N), np.float32)
+    s1 = (rs.randn(1, M + 1, N, N) + 1j * rs.randn(1, M + 1, N, N)).astype(np.complex64)
+    s2 = (rs.randn(1, M + 1, 2 * N, N) + 1j * rs.randn(1, M + 1, 2 * N, N)).astype(np.complex64)
+    fwd = plan.run(x, 1, M, [0], mask=2, s1=s1.copy())[2]
+    ref = np.fft.fft(s1.astype(np.complex128), n=2 * N, axis=2)
+    assert np.linalg.norm(fwd - ref) <= 1e-6 * np.linalg.norm(ref)
+    inv = plan.run(x, 1, M, [0], mask=8, s2=s2.copy())[1]
+    ref = (np.fft.ifft(s2.astype(np.complex128), axis=2) * (2 * N))[:, :, :N]
+    assert np.linalg.norm(inv - ref) <= 1e-6 * np.linalg.norm(ref)
+    assert np.array_equal(fwd, plan.run(x, 1, M, [0], mask=2, s1=s1.copy(), reverse=True)[2])
+    assert np.array_equal(inv, plan.run(x, 1, M, [0], mask=8, s2=s2.copy(), reverse=True)[1])
+
+
 def test_operator_structure_is_validated():
     """The kernels look for rows longer than three taps only among the first few rows of mtx and never in
     mtx^T (lct_tables.h); an operator that breaks this must be refused, not silently truncated."""
