@@ -93,6 +93,7 @@ template <int N, class Launcher> int launch_row_inv(const Params& p, Launcher& l
 template <int N, class Launcher> int launch_col_filter(const Params& p, Launcher& l) {
     // 512-point lines: two 256-point transforms by output parity (16-wide butterflies): 564 vs 682 us at cfg5, 5 % ahead
     // with four channels.  At N = 128 the register-cached filter of ColFilter wins clearly (288 vs 460 us at cfg4).
+    // (The two parities side by side in one warp, as the H-axis kernels do it, measured slower here: 673-795 vs 560 us.)
     if constexpr (N >= 256) {
         using PL = typename LinePlan<N>::type;
         return l.template launch<ColFilterSplit<PL, 256 / PL::TL>>(p);
