@@ -71,6 +71,8 @@ template <int M, class Launcher> int launch_time_fwd(const Params& p, Launcher& 
     else
         return l.template launch<TimeFwd<P, TimeTile<M>::CT>>(p);
 }
+// (M = 512 as two 256-point inverses by input parity, side by side in a 1024-thread block like the H-axis kernels
+//  at N = 256, measured slower: 268 vs 230 us at cfg3, 143 vs 124 us at cfg5)
 template <int M, class Launcher> int launch_time_inv(const Params& p, Launcher& l) {
     return l.template launch<TimeInv<typename TimeInvPlan<M>::type, TimeTile<M>::CT>>(p);
 }
