@@ -1130,6 +1130,21 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
     static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) {
         TwP::fill(smem, tid, kThreads);
     }
+#ifndef LCT_PLANE_GROUPSYNC
+#define LCT_PLANE_GROUPSYNC 2
+#endif
+    // During the W pass a row is shared by the TL warps that hold its line threads: with 64-row batches and 32-lane
+    // warps those are the even warps (rows 0..31 of a batch) or the odd warps (rows 32..63).  The two sets touch
+    // disjoint rows of T and X, so between W phases each set synchronises on its own named barrier and the sets drift
+    // apart -- one can be in its shared-memory burst while the other is in its butterflies.
+    static constexpr bool kGroupSync = LCT_PLANE_GROUPSYNC && RBt == 64 && RBt * PWp::TL == kThreads;
+    static constexpr int kGroupThreads = kThreads / 2;
+    // The same two warp sets own disjoint column halves in the H passes (64-column batches), so the barrier between
+    // the two H stages is a set barrier as well; only the H <-> W turns need the whole block.
+    static constexpr bool kGroupSyncH = (LCT_PLANE_GROUPSYNC >= 2) && kGroupSync && CB == 64 && nHB == 1;
+    static constexpr bool group_phase(int ph) {
+        return (kGroupSync && ph >= 2 && ph < 2 + 3 * nWB - 1) || (kGroupSyncH && (ph == 0 || ph == 2 + 3 * nWB));
+    }
 
     template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem, int tid, int bx, int by, int) {
         float2* T = reinterpret_cast<float2*>(smem + kTwBytes);
@@ -1240,11 +1255,21 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
 template <class K, class = void> struct has_prologue { static constexpr bool value = false; };
 template <class K> struct has_prologue<K, decltype((void)K::kHasPrologue)> { static constexpr bool value = true; };
 
+template <class K, class = void> struct has_group_sync { static constexpr bool value = false; };
+template <class K> struct has_group_sync<K, decltype((void)K::kGroupSync)> { static constexpr bool value = true; };
+
 #ifndef LCT_EMULATE
 template <class K, int PH> struct PhaseLoop {
     static LCT_DEV void run(const Params& p, typename K::Regs& r, unsigned char* smem, int it) {
         K::template phase<PH>(p, r, smem, threadIdx.x, blockIdx.x, blockIdx.y, it);
-        if constexpr (K::kWarpSync) __syncwarp(); else __syncthreads();
+        if constexpr (K::kWarpSync) __syncwarp();
+        else if constexpr (has_group_sync<K>::value) {
+            if constexpr (K::group_phase(PH))
+                if ((threadIdx.x >> 5) & 1) asm volatile("bar.sync 2, %0;" ::"n"(K::kGroupThreads) : "memory");
+                else asm volatile("bar.sync 1, %0;" ::"n"(K::kGroupThreads) : "memory");
+            else __syncthreads();
+        }
+        else __syncthreads();
         if constexpr (PH + 1 < K::kPhases) PhaseLoop<K, PH + 1>::run(p, r, smem, it);
     }
 };
