@@ -796,7 +796,8 @@ template <class P, int CT_> struct RowInv {
 // (the inverse adds the halves in a third phase).  16-wide butterflies at 64 registers and two 512-thread blocks
 // per SM instead of 32-wide ones at 128 registers: cfg5 K2 240 -> 184 us, K4 225 -> 196 us.  (Running the parities
 // one after the other through one buffer measured 196 us forward and, with the even half parked in the output
-// rows, 251 us inverse.)  P is the N-point plan; S2 rows stay in natural kh order, so K3 is unchanged.
+// rows, 251 us inverse.  Per-half named barriers between the stages, as in the plane kernel: K2 182 us, K4 218 us -- kept out.)
+// P is the N-point plan; S2 rows stay in natural kh order, so K3 is unchanged.
 // ---------------------------------------------------------------------------
 template <class P, int CT_> struct RowFwdSplit {
     static_assert(P::S == 2, "RowFwdSplit needs a two-stage plan");
@@ -1139,6 +1140,7 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
     // apart -- one can be in its shared-memory burst while the other is in its butterflies.
     static constexpr bool kGroupSync = LCT_PLANE_GROUPSYNC && RBt == 64 && RBt * PWp::TL == kThreads;
     static constexpr int kGroupThreads = kThreads / 2;
+    static LCT_DEV int group_of(int tid) { return (tid >> 5) & 1; }
     // The same two warp sets own disjoint column halves in the H passes (64-column batches), so the barrier between
     // the two H stages is a set barrier as well; only the H <-> W turns need the whole block.
     static constexpr bool kGroupSyncH = (LCT_PLANE_GROUPSYNC >= 2) && kGroupSync && CB == 64 && nHB == 1;
@@ -1265,7 +1267,7 @@ template <class K, int PH> struct PhaseLoop {
         if constexpr (K::kWarpSync) __syncwarp();
         else if constexpr (has_group_sync<K>::value) {
             if constexpr (K::group_phase(PH))
-                if ((threadIdx.x >> 5) & 1) asm volatile("bar.sync 2, %0;" ::"n"(K::kGroupThreads) : "memory");
+                if (K::group_of(threadIdx.x)) asm volatile("bar.sync 2, %0;" ::"n"(K::kGroupThreads) : "memory");
                 else asm volatile("bar.sync 1, %0;" ::"n"(K::kGroupThreads) : "memory");
             else __syncthreads();
         }
