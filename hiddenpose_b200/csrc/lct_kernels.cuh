@@ -19,6 +19,9 @@
 //                reduces the volume's per-channel min/max for normalize_feature.
 //   PlaneFilter  K2 + K3 + K4 in one kernel with the (c, kt) plane resident in shared memory;
 //                used whenever the plane fits (N <= 64).
+//   RowFwdSplit / ColFilterSplit / RowInvSplit
+//                K2 / K3 / K4 for 512-point lines (N = 256): the zero-extended transform as two
+//                256-point transforms by output parity (16-wide butterflies instead of 32-wide).
 //
 // The backward pass is the same chain with conj(filter), the falloff moved
 // from K1's input to K5's output and the window cut out at the end
