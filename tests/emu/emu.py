@@ -52,7 +52,7 @@ class EmuPlan:
         self.filt_plane = (np.ascontiguousarray(self.filt[:, kh, :].reshape(M + 1, L, N, 2).transpose(0, 2, 1, 3))
                            if N <= 64 else None)
 
-    def run(self, inp, D, Tin, be, backward=False, mask=31, reverse=False, s1=None, s2=None, fused=True):
+    def run(self, inp, D, Tin, be, backward=False, mask=31, reverse=False, s1=None, s2=None, fused=True, drift=0):
         M, N = self.M, self.N
         inp = np.ascontiguousarray(inp, dtype=np.float32)
         C = inp.shape[0]
@@ -67,6 +67,7 @@ class EmuPlan:
         be = np.asarray(be, dtype=np.int32)
         uniform = bool(np.all(be == be[0]))
         f, i32 = ctypes.c_float, ctypes.c_int
+        lib().lct_emu_set_drift(int(drift))        # 1 / 2: one warp set runs whole runs of set-barrier phases before the other
         rc = lib(reverse).lct_emu_run(
             M, N, C, D, Tin, int(be[0]), None if uniform else _p(be, i32),
             _p(inp, f), _p(out, f), _p(s1.view(np.float32), f), _p(s2.view(np.float32), f),
@@ -74,5 +75,6 @@ class EmuPlan:
             _p(self.filt.view(np.float32), f),
             _p(self.filt_plane.view(np.float32), f) if (fused and self.filt_plane is not None) else None,
             int(backward), int(mask))
+        lib().lct_emu_set_drift(0)
         assert rc == 0, rc
         return out, s1, s2

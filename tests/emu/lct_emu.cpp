@@ -7,7 +7,9 @@
 #define LCT_EMULATE 1
 #include <cmath>
 #include <cstring>
+#include <array>
 #include <limits>
+#include <utility>
 #include <vector>
 
 #include "lct_chain.cuh"
@@ -31,6 +33,43 @@ template <class K, int PH> struct EmuPhases {
     }
 };
 
+// Set-barrier drift: kernels that synchronise warp sets on named barriers between some phases (K::group_phase)
+// claim that the sets are independent until the next whole-block barrier.  In drift mode one set runs through the
+// whole run of such phases before the other starts -- the largest skew the hardware could produce.
+int g_drift = 0;                  // 0 = off, 1 = set 0 first, 2 = set 1 first
+
+template <class K, int PH> void run_phase_of_set(const lct::Params& p, std::vector<typename K::Regs>& regs, unsigned char* smem,
+                                                 int bx, int by, int it, int set) {
+    for (int i = 0; i < K::kThreads; ++i) {
+        const int tid = g_reverse_threads ? K::kThreads - 1 - i : i;
+        if constexpr (lct::has_group_sync<K>::value) {
+            if (set >= 0 && K::group_of(tid) != set) continue;
+        }
+        K::template phase<PH>(p, regs[tid], smem, tid, bx, by, it);
+    }
+}
+template <class K> using PhaseFn = void (*)(const lct::Params&, std::vector<typename K::Regs>&, unsigned char*, int, int, int, int);
+template <class K, int... I> std::array<PhaseFn<K>, sizeof...(I)> phase_table(std::integer_sequence<int, I...>) {
+    return {{&run_phase_of_set<K, I>...}};
+}
+template <class K> void run_phases_drifting(const lct::Params& p, std::vector<typename K::Regs>& regs, unsigned char* smem,
+                                            int bx, int by, int it) {
+    if constexpr (lct::has_group_sync<K>::value) {
+        const auto table = phase_table<K>(std::make_integer_sequence<int, K::kPhases>{});
+        int ph = 0;
+        while (ph < K::kPhases) {
+            if (!K::group_phase(ph)) { table[ph](p, regs, smem, bx, by, it, -1); ++ph; continue; }
+            int e = ph;
+            while (e < K::kPhases - 1 && K::group_phase(e)) ++e;          // phase e ends with a whole-block barrier
+            for (int k = 0; k < 2; ++k) {
+                const int set = g_drift == 1 ? k : 1 - k;
+                for (int q = ph; q <= e; ++q) table[q](p, regs, smem, bx, by, it, set);
+            }
+            ph = e + 1;
+        }
+    }
+}
+
 struct EmuLauncher {
     void mark(int) {}
     template <class K> int launch(const lct::Params& p0) {
@@ -53,7 +92,10 @@ struct EmuLauncher {
                         for (int tid = K::kThreads - 1; tid >= 0; --tid) K::prologue(p, regs[tid], smem.data(), tid, bx, by);
                 }
                 std::memset(smem.data() + K::kSmem, 0xA5, 64);
-                for (int it = 0; it < iters; ++it) EmuPhases<K, 0>::run(p, regs, smem.data(), bx, by, it);
+                for (int it = 0; it < iters; ++it) {
+                    if (g_drift && lct::has_group_sync<K>::value) run_phases_drifting<K>(p, regs, smem.data(), bx, by, it);
+                    else EmuPhases<K, 0>::run(p, regs, smem.data(), bx, by, it);
+                }
                 for (int g = 0; g < 64; ++g)
                     if (smem[K::kSmem + g] != 0xA5) return 200;      // shared-memory overrun
             }
@@ -73,6 +115,8 @@ void lct_emu_init(int reverse_threads) {
         lct::h_tw[j].y = (float)std::sin(a);
     }
 }
+
+void lct_emu_set_drift(int mode) { g_drift = mode; }
 
 // All pointers are host pointers.  `filt` must already carry the 1/(8 M N N) scale.  The operator
 // arrives as the CSR of mtx plus the falloff vector, exactly as lct_plan_create receives it.

@@ -163,6 +163,23 @@ def test_emulated_parity_split_row_kernels():
     assert np.array_equal(inv, plan.run(x, 1, M, [0], mask=8, s2=s2.copy(), reverse=True)[1])
 
 
+@pytest.mark.parametrize("N", [32, 64])
+def test_emulated_set_barriers_tolerate_maximal_drift(N):
+    """The plane kernel synchronises its two warp sets on named 256-thread barriers between the phases that only
+    involve one set (PlaneFilter::group_phase).  The emulator's drift mode runs one set through every run of such
+    phases before the other starts: the largest skew the hardware could produce must not change a bit (a wrongly
+    declared set barrier shows up as NaN from the poisoned shared memory)."""
+    from tests.emu.emu import EmuPlan
+    M = 32
+    plan = EmuPlan(N, M, 0.16)
+    x = np.random.RandomState(3).rand(2, M, N, N).astype(np.float32)
+    base = plan.run(x, 1, M, [0, 0])[0]
+    assert not np.isnan(base).any()
+    for drift in (1, 2):
+        assert np.array_equal(base, plan.run(x, 1, M, [0, 0], drift=drift)[0])
+        assert np.array_equal(base, plan.run(x, 1, M, [0, 0], drift=drift, reverse=True)[0])
+
+
 def test_operator_structure_is_validated():
     """The kernels look for rows longer than three taps only among the first few rows of mtx and never in
     mtx^T (lct_tables.h); an operator that breaks this must be refused, not silently truncated."""
