@@ -81,6 +81,8 @@ CASES = [
     ("m128n32_window",   32, 128, 1, 2, 20, 120, "lct", "diffuse",  False),   # reference class verbatim (crop 128)
     ("m128n128_full",   128, 128, 1, 1,  0, 128, "lct", "diffuse",  False),   # reference training shape, verbatim class
     ("m256n64_full",     64, 256, 1, 1,  0, 256, "lct", "diffuse",  False),   # BASELINE config 1/2 shape
+    ("m32n256_window",  256,  32, 1, 1,  2,  29, "lct", "diffuse",  False),   # 512-point spatial lines: the parity-split K2/K3/K4
+    ("m512n16_window",   16, 512, 1, 2,  5, 500, "lct", "diffuse",  False),   # 512 time bins: the 32-wide time kernels
 ]
 
 
@@ -90,9 +92,16 @@ def bin_len_for(M):
 
 
 def main():
+    only = set(sys.argv[1:])          # case names to (re)generate; none = everything, constants included
     ref_lct, lct_cropfix, helper = load_reference()
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if not only:
+        write_constants(helper)
+    write_cases(ref_lct, lct_cropfix, only)
+
+
+def write_constants(helper):
 
     # ---- constants -------------------------------------------------------
     const = {}
@@ -114,8 +123,13 @@ def main():
     np.savez_compressed(os.path.join(HERE, "constants.npz"), **const)
     print("constants.npz written")
 
+
+
+def write_cases(ref_lct, lct_cropfix, only):
     # ---- forward / backward ---------------------------------------------
     for seed, (name, N, M, B, D, tbe, ten, method, material, full) in enumerate(CASES):
+        if only and name not in only:
+            continue
         cls = ref_lct if M == 128 else lct_cropfix
         layer = cls(spatial=N, crop=M, bin_len=bin_len_for(M), wall_size=2.0, method=method, material=material)
         assert layer.crop == M
