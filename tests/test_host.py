@@ -117,7 +117,7 @@ def test_shared_library_exports_every_declared_symbol():
 
 
 # ---- kernel logic through the CPU thread emulator -----------------------------------
-@pytest.mark.parametrize("name", ["m32n8_full", "m64n16_full", "m64n16_window", "m64n16_specular"])
+@pytest.mark.parametrize("name", ["m32n8_full", "m64n16_full", "m64n16_window", "m64n16_specular", "m512n16_window", "m32n256_window"])
 def test_emulated_kernels_match_reference(name):
     """The exact device code, stepped thread by thread on the CPU, vs the reference's outputs."""
     from tests.emu.emu import EmuPlan
