@@ -116,6 +116,15 @@ template <class T> int to_device(const T* host, size_t count, T** out) {
     return LCT_OK;
 }
 
+// Per-sample window begins travel to the device as kernel parameters (256 per launch), not as a copy from the
+// caller's pageable array: a parameter block is captured by value, so ragged windows are legal under stream
+// capture (a CUDA graph replays the windows it was captured with) and nothing reads host memory after the call.
+constexpr int kWindowChunk = 256;
+struct WindowChunk { int v[kWindowChunk]; };
+__global__ void set_windows_kernel(int* dst, const WindowChunk w, int n) {
+    if ((int)threadIdx.x < n) dst[threadIdx.x] = w.v[threadIdx.x];
+}
+
 __global__ void scale_filter_kernel(float2* f, size_t n, float s) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float2 v = f[i];
@@ -181,9 +190,29 @@ struct lct_plan {
     static constexpr int kMaxGroups = 8;
     int groups = 1;
     int prefetch_ahead = 0;                 // SM count, or 0 when LCT_L2_PREFETCH=0 (see GpuLauncher::prefetch_ahead)
-    cudaStream_t side[kMaxGroups] = {};
-    cudaEvent_t fork = nullptr, join[kMaxGroups] = {};
-    mutable std::mutex side_mutex;          // the side streams/events are shared by all callers of the plan
+    // One set of side streams + fork/join events per caller stream (created up front, handed out first come first
+    // served): two threads driving the plan on two streams get two sets, so neither waits on the other's kernels.
+    // More distinct caller streams than sets share sets round robin -- still correct (every use is ordered by its
+    // own fork/join events), only then with a false dependency between the sharers.
+    static constexpr int kSideSets = 4;
+    struct SideSet {
+        cudaStream_t side[kMaxGroups] = {};
+        cudaEvent_t fork = nullptr, join[kMaxGroups] = {};
+        cudaStream_t owner = nullptr;
+        bool owned = false;
+    };
+    mutable SideSet sets[kSideSets];
+    mutable int next_set = 0;
+    mutable std::mutex side_mutex;          // guards the set table and the enqueue order on a set
+    SideSet& set_for(cudaStream_t caller) const {       // call with side_mutex held
+        for (int i = 0; i < kSideSets; ++i)
+            if (sets[i].owned && sets[i].owner == caller) return sets[i];
+        for (int i = 0; i < kSideSets; ++i)
+            if (!sets[i].owned) { sets[i].owned = true; sets[i].owner = caller; return sets[i]; }
+        SideSet& s = sets[next_set];
+        next_set = (next_set + 1) % kSideSets;
+        return s;
+    }
     float2* filt = nullptr;         // natural layout (unfused K3), or
     float2* filt_plane = nullptr;   // [kt][kw][plane row] (plane-fused kernel); exactly one of the two is set
     bool fused() const { return filt_plane != nullptr; }
@@ -230,11 +259,13 @@ void lct_plan_destroy(lct_plan* plan) {
     plan->mtx_falloff.release(); plan->mtx.release(); plan->mtxi.release(); plan->mtxi_falloff.release();
     cudaFree(plan->filt);
     cudaFree(plan->filt_plane);
-    for (int g = 0; g < lct_plan::kMaxGroups; ++g) {
-        if (plan->side[g]) cudaStreamDestroy(plan->side[g]);
-        if (plan->join[g]) cudaEventDestroy(plan->join[g]);
+    for (auto& set : plan->sets) {
+        for (int g = 0; g < lct_plan::kMaxGroups; ++g) {
+            if (set.side[g]) cudaStreamDestroy(set.side[g]);
+            if (set.join[g]) cudaEventDestroy(set.join[g]);
+        }
+        if (set.fork) cudaEventDestroy(set.fork);
     }
-    if (plan->fork) cudaEventDestroy(plan->fork);
     delete plan;
 }
 
@@ -316,16 +347,18 @@ int lct_plan_create(const lct_desc* d, lct_plan** out) {
         const char* env = std::getenv("LCT_STREAM_GROUPS");
         int g = env ? std::atoi(env) : LCT_DEFAULT_STREAM_GROUPS;
         p->groups = g < 1 ? 1 : (g > lct_plan::kMaxGroups ? lct_plan::kMaxGroups : g);
-        for (int i = 1; i < p->groups; ++i) {
-            if (cudaStreamCreateWithFlags(&p->side[i], cudaStreamNonBlocking) != cudaSuccess ||
-                cudaEventCreateWithFlags(&p->join[i], cudaEventDisableTiming) != cudaSuccess) {
-                lct_plan_destroy(p);
-                return fail(LCT_ERR_CUDA, "side stream creation");
+        for (auto& set : p->sets) {
+            for (int i = 1; i < p->groups; ++i) {
+                if (cudaStreamCreateWithFlags(&set.side[i], cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&set.join[i], cudaEventDisableTiming) != cudaSuccess) {
+                    lct_plan_destroy(p);
+                    return fail(LCT_ERR_CUDA, "side stream creation");
+                }
             }
-        }
-        if (p->groups > 1 && cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming) != cudaSuccess) {
-            lct_plan_destroy(p);
-            return fail(LCT_ERR_CUDA, "fork event creation");
+            if (p->groups > 1 && cudaEventCreateWithFlags(&set.fork, cudaEventDisableTiming) != cudaSuccess) {
+                lct_plan_destroy(p);
+                return fail(LCT_ERR_CUDA, "fork event creation");
+            }
         }
     }
     cudaError_t e = cudaDeviceSynchronize();
@@ -370,7 +403,13 @@ static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const 
     int* be_dev = nullptr;
     if (!uniform) {
         be_dev = reinterpret_cast<int*>(base);
-        LCT_CUDA(cudaMemcpyAsync(be_dev, tbe, sizeof(int) * B, cudaMemcpyHostToDevice, stream));
+        for (int b0 = 0; b0 < B; b0 += kWindowChunk) {
+            WindowChunk w;
+            const int n = B - b0 < kWindowChunk ? B - b0 : kWindowChunk;
+            std::memcpy(w.v, tbe + b0, sizeof(int) * n);
+            set_windows_kernel<<<1, kWindowChunk, 0, stream>>>(be_dev + b0, w, n);
+        }
+        LCT_CUDA(cudaGetLastError());
     }
     float2* s1 = reinterpret_cast<float2*>(base + header);
     float2* s2 = s1 + (size_t)chunk * (M + 1) * N * N;
@@ -382,24 +421,39 @@ static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const 
     if (plan->groups > 1 && chunk >= C && C >= 2 && !events) {     // per-kernel events need the single-stream order
         // one batch: split the channels into groups, each an independent chain on its own stream
         std::lock_guard<std::mutex> lock(plan->side_mutex);
+        lct_plan::SideSet& set = plan->set_for(stream);
         const int G = (int)(C < plan->groups ? C : plan->groups);
-        LCT_CUDA(cudaEventRecord(plan->fork, stream));
-        for (int g = 0; g < G; ++g) {
+        LCT_CUDA(cudaEventRecord(set.fork, stream));
+        // Whatever fails below, every side stream that was given work is joined back into the caller's stream
+        // before the error is returned: the caller is free to release the buffers as soon as its own stream has
+        // passed this call, so nothing may be left running unordered on a side stream.
+        int status = LCT_OK, forked = 0;
+        for (int g = 0; g < G && status == LCT_OK; ++g) {
             const long long c0 = C * g / G, c1 = C * (g + 1) / G;
-            cudaStream_t sg = g == 0 ? stream : plan->side[g];
-            if (g) LCT_CUDA(cudaStreamWaitEvent(sg, plan->fork, 0));
+            cudaStream_t sg = g == 0 ? stream : set.side[g];
+            if (g) {
+                const cudaError_t e = cudaStreamWaitEvent(sg, set.fork, 0);
+                if (e != cudaSuccess) { status = fail(LCT_ERR_CUDA, "cudaStreamWaitEvent(fork)", e); break; }
+                forked = g;
+            }
             GpuLauncher lg{sg, plan->device};
             lg.prefetch_ahead = plan->prefetch_ahead;
             const int rc = lct::run_chain(lg, t, M, N, (int)(c1 - c0), D, Tin, tbe[0], be_dev, (int)c0,
                                           in + (size_t)c0 * in_stride, out + (size_t)c0 * out_stride,
                                           s1 + (size_t)c0 * (M + 1) * N * N, s2 + (size_t)c0 * (M + 1) * 2 * N * N, backward,
                                           lct::kStageAll, minmax_keys);
-            if (rc < 0) return fail(LCT_ERR_UNSUPPORTED, "size not compiled");
-            if (rc) return fail(LCT_ERR_CUDA, "kernel launch", lg.err);
-            if (g) LCT_CUDA(cudaEventRecord(plan->join[g], sg));
+            if (rc < 0) status = fail(LCT_ERR_UNSUPPORTED, "size not compiled");
+            else if (rc) status = fail(LCT_ERR_CUDA, "kernel launch", lg.err);
         }
-        for (int g = 1; g < G; ++g) LCT_CUDA(cudaStreamWaitEvent(stream, plan->join[g], 0));
-        return LCT_OK;
+        for (int g = 1; g <= forked; ++g) {
+            cudaError_t e = cudaEventRecord(set.join[g], set.side[g]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, set.join[g], 0);
+            if (e != cudaSuccess) {
+                cudaStreamSynchronize(set.side[g]);         // last resort: the join could not be expressed as an event
+                if (status == LCT_OK) status = fail(LCT_ERR_CUDA, "side stream join", e);
+            }
+        }
+        return status;
     }
     GpuLauncher l{stream, plan->device};
     l.events = events;

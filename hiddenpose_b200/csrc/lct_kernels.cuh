@@ -242,7 +242,8 @@ struct TileWalk {
 // order-preserving key of a float and its position (see lct_normalize.cuh)
 LCT_DEV unsigned long long minmax_key(float v, unsigned int pos, bool is_max) {
     const unsigned int b = (unsigned int)float_bits(v);
-    const unsigned int k = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    unsigned int k = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    if (v != v) k = is_max ? 0xffffffffu : 0u;         // NaN wins both reductions (torch.min / torch.max propagate it)
     return is_max ? ~(((unsigned long long)k << 32) | (0xffffffffu - pos)) : (((unsigned long long)k << 32) | pos);
 }
 LCT_DEV void minmax_commit(unsigned long long* keys, int c, unsigned long long kmin, unsigned long long kmax) {
@@ -668,20 +669,35 @@ template <class P, int CT_> struct TimeInv {
                 for (int m = 0; m < M / P::TL; ++m, d += step)
                     if (tau + m * P::TL < p.out_T) *d = band_dot<false>(p, er, m * P::TL, vc);
             } else {
-                float mn = 3.4e38f, mx = -3.4e38f;
-                int jmn = 0, jmx = 0;
+                // Ordered compares never select a NaN and the +-3.4e38 starting values hide an infinity, so the loop
+                // also folds every value into `poison` (v * 0 is 0 for finite v and NaN otherwise: one FFMA per
+                // value); a poisoned strip redoes its reduction on the integer keys, where NaN and +-inf are ordered.
+                float mn = 3.4e38f, mx = -3.4e38f, poison = 0.f;
+                int jmn = tau, jmx = tau;
 #ifndef LCT_EMULATE
 #pragma unroll 4
 #endif
                 for (int j = tau; j < p.out_T; j += P::TL, d += step) {
                     const float v = band_dot<false>(p, ell, be + j, vc);
                     *d = v;
+                    poison = fmaf(v, 0.f, poison);
                     if (v < mn) { mn = v; jmn = j; }
                     if (v > mx) { mx = v; jmx = j; }
                 }
                 const unsigned int base = (unsigned int)(col0 + col);
-                minmax_commit(p.minmax_keys, p.c_base + c, minmax_key(mn, (unsigned int)jmn * NN + base, false),
-                              minmax_key(mx, (unsigned int)jmx * NN + base, true));
+                unsigned long long kmin = minmax_key(mn, (unsigned int)jmn * NN + base, false);
+                unsigned long long kmax = minmax_key(mx, (unsigned int)jmx * NN + base, true);
+                if (poison != 0.f) {                       // NaN or infinity somewhere in this thread's strip
+                    kmin = ~0ull; kmax = ~0ull;
+                    for (int j = tau; j < p.out_T; j += P::TL) {
+                        const float v = band_dot<false>(p, ell, be + j, vc);
+                        const unsigned long long a = minmax_key(v, (unsigned int)j * NN + base, false);
+                        const unsigned long long b = minmax_key(v, (unsigned int)j * NN + base, true);
+                        kmin = a < kmin ? a : kmin;
+                        kmax = b < kmax ? b : kmax;
+                    }
+                }
+                if (tau < p.out_T) minmax_commit(p.minmax_keys, p.c_base + c, kmin, kmax);
             }
         }
     }

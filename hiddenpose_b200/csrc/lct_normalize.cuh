@@ -9,6 +9,9 @@
 //
 // min/max are carried as 64-bit keys  (order-preserving float bits << 32 | position)  reduced with
 // atomicMin: the max side stores the complemented key.  Ties resolve to the lowest position.
+// NaN wins both reductions, as it does in torch.min / torch.max (a diverged volume must turn the whole
+// normalised output to NaN, as in the reference, not to finite garbage): it is keyed below -inf on the
+// min side and above +inf on the max side, and both keys decode to a NaN.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -24,10 +27,12 @@ __device__ __forceinline__ float float_from_order_key(unsigned int k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 __device__ __forceinline__ unsigned long long min_key(float v, unsigned int pos) {
-    return ((unsigned long long)float_order_key(v) << 32) | pos;
+    const unsigned int k = (v != v) ? 0u : float_order_key(v);                 // key 0 decodes to a NaN
+    return ((unsigned long long)k << 32) | pos;
 }
 __device__ __forceinline__ unsigned long long max_key(float v, unsigned int pos) {       // stored complemented
-    return ~(((unsigned long long)float_order_key(v) << 32) | (0xffffffffu - pos));
+    const unsigned int k = (v != v) ? 0xffffffffu : float_order_key(v);        // key ~0 decodes to a NaN
+    return ~(((unsigned long long)k << 32) | (0xffffffffu - pos));
 }
 __device__ __forceinline__ void key_min_value(unsigned long long k, float& v, unsigned int& pos) {
     v = float_from_order_key((unsigned int)(k >> 32));

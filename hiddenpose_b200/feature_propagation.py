@@ -46,10 +46,16 @@ class FeaturePropagation(nn.Module):
     def forward(self, x, time_begin, time_end):
         return self.method(x, time_begin, time_end)
 
+    def forward_normalized(self, x, time_begin, time_end):
+        """``normalize_feature(self(x, time_begin, time_end))`` -- the two lines NlosPose.py:53-54 -- with the
+        min / max passed explicitly from the LCT's last kernel to the affine pass (no state left on tensors)."""
+        y, keys = self.method.forward_with_minmax(x, time_begin, time_end)
+        return normalize_feature(y, minmax=keys)
 
-def _native_normalize(x, scale):
-    from .lct_function import NormalizeFeatureFunction
-    return NormalizeFeatureFunction.apply(x.contiguous(), scale, getattr(x, "_lct_minmax", None))
+
+def _native_normalize(x, scale, minmax=None):
+    from .lct_function import NormalizeFeatureFunction, recall_minmax
+    return NormalizeFeatureFunction.apply(x.contiguous(), scale, minmax if minmax is not None else recall_minmax(x))
 
 
 def normalize(data_bxcxdxhxw):
@@ -62,15 +68,17 @@ def normalize(data_bxcxdxhxw):
     return (shifted / (shifted.max(2, keepdim=True)[0] + 1e-15)).view(b, c, d, h, w)
 
 
-def normalize_feature(data_bxcxdxhxw):
+def normalize_feature(data_bxcxdxhxw, minmax=None):
     """feature_propagation.py:273-286: min/max normalisation times 10.
 
     The reference calls ``nn.ReLU()(x)`` and discards the result (line 274), so
     negative LCT values do reach the ``min``; that behaviour is kept.  CUDA float32 volumes go through
-    the library (``lct_normalize_feature``; the LCT layer hands over min/max it already reduced).
+    the library (``lct_normalize_feature``).  ``minmax`` (optional, not in the reference's signature) is the
+    key tensor ``LCT.forward_with_minmax`` returned for exactly this volume; without it the keys the layer
+    remembered for this tensor object are used if it is untouched since, else one reduction pass finds them.
     """
     if data_bxcxdxhxw.is_cuda and data_bxcxdxhxw.dtype == torch.float32 and data_bxcxdxhxw.dim() == 5:
-        return _native_normalize(data_bxcxdxhxw, 10.0)
+        return _native_normalize(data_bxcxdxhxw, 10.0, minmax)
     return normalize(data_bxcxdxhxw) * 10.0
 
 

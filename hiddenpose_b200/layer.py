@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 
 from . import operators as ops
-from .lct_function import LctFunction, LctPlan
+from .lct_function import LctFunction, LctPlan, remember_minmax
 
 
 def _as_device(dev):
@@ -58,10 +58,27 @@ class LctLayerBase(nn.Module):
         self._host_filter = os.environ.get("HIDDENPOSE_LCT_HOST_FILTER", "0") not in ("", "0")
         self._lapw = ops.laplacian_filter() if method == "bp" else None       # tflct.py:73-77
         self._plan, self._dev, self.dnum = None, torch.device("cpu"), 2
-        # reduce the volume's per-channel min/max in the last kernel and leave them on the output for
+        # reduce the volume's per-channel min/max in the last kernel and remember them for
         # normalize_feature (FeaturePropagation turns this on: NlosPose.py:53-54 always normalises next)
         self.fuse_minmax = False
-        self._dense_cache = {}
+
+    # -- pickling / copying ---------------------------------------------------------------
+    # The reference ends training with ``torch.save(model, path)`` (train.py:223) and EMA helpers deep-copy
+    # the model.  The device plan is a native handle (not picklable, not copyable): it is dropped from the
+    # state and rebuilt from the host constants on the next ``forward`` / ``todev`` of the copy.
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_plan"] = None
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._plan = None
+
+    def _ensure_plan(self):
+        if self._plan is None and self._dev.type == "cuda":
+            self.todev(self._dev, self.dnum)
+        return self._plan
 
     @property
     def _filter_half(self):
@@ -154,17 +171,40 @@ class LctLayerBase(nn.Module):
         if dnum != self.dnum:
             # the reference fails here too (datapad sized by todev's dnum, tflct.py:83,133,140)
             raise RuntimeError(f"input has {dnum} channels but the layer was sized with todev(dev, dnum={self.dnum})")
-        if self._plan is None or not feture_bxdxtxhxw.is_cuda:
+        y, keys = self._run(feture_bxdxtxhxw, tbes, tens, self.fuse_minmax)
+        if keys is not None:
+            remember_minmax(y, keys)         # implicit hand-off to a following normalize_feature(y) call
+        return y
+
+    def forward_with_minmax(self, feture_bxdxtxhxw, tbes, tens):
+        """``forward`` that also returns the per-channel min / max keys its last kernel reduced
+        (``(B * D, 2)`` int64, the format ``lct_normalize_feature`` takes): the explicit form of the
+        hand-off, ``normalize_feature(y, minmax=keys)``.  Keys are ``None`` for ``method='bp'``."""
+        bnum, dnum, tnum, hnum, wnum = feture_bxdxtxhxw.shape
+        for tbe, ten in zip(tbes, tens):
+            assert tbe >= 0
+            assert ten <= self._M
+        assert hnum == wnum
+        assert hnum == self._N
+        tbes, tens = self._windows(tbes, tens, bnum, tnum)
+        if dnum != self.dnum:
+            raise RuntimeError(f"input has {dnum} channels but the layer was sized with todev(dev, dnum={self.dnum})")
+        return self._run(feture_bxdxtxhxw, tbes, tens, True)
+
+    def _run(self, x, tbes, tens, want_minmax):
+        plan = self._ensure_plan()
+        if plan is None or not x.is_cuda:
             raise RuntimeError("hiddenpose_b200 LCT runs on CUDA only (no CPU fallback): call todev('cuda', dnum) "
                                "and pass a CUDA tensor")
-        if feture_bxdxtxhxw.device != self._plan.device:
-            raise RuntimeError(f"input is on {feture_bxdxtxhxw.device} but the layer was moved to {self._plan.device}")
-        x = feture_bxdxtxhxw.contiguous().float()
-        if self.fuse_minmax and self._lapw is None:
-            y, keys = LctFunction.apply(x, self._plan, tbes, tens, True)
-            y._lct_minmax = (keys, y._version, y.data_ptr())
-            return y
-        return LctFunction.apply(x, self._plan, tbes, tens)
+        if x.device != plan.device:
+            raise RuntimeError(f"input is on {x.device} but the layer was moved to {plan.device}")
+        if x.dtype != torch.float32:
+            # the reference multiplies by float32 constants (tflct.py:127,138): any other dtype fails there too
+            raise RuntimeError(f"expected a float32 input, got {x.dtype} (the layer's constants are float32, as in the reference)")
+        x = x.contiguous()
+        if want_minmax and self._lapw is None:
+            return LctFunction.apply(x, plan, tbes, tens, True)
+        return LctFunction.apply(x, plan, tbes, tens), None
 
     @staticmethod
     def _windows(tbes, tens, bnum, tnum):

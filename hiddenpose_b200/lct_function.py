@@ -7,11 +7,41 @@ saved for backward except the integer window.
 from __future__ import annotations
 
 import ctypes
+import weakref
 
 import numpy as np
 import torch
 
 from . import _native
+
+
+# -- implicit min/max hand-off ------------------------------------------------------------------
+# FeaturePropagation's caller applies normalize_feature to the very tensor the layer returned
+# (NlosPose.py:53-54).  The layer's last kernel has already reduced that tensor's per-channel min / max;
+# they are remembered here per tensor *object* (weak reference: the entry dies with the tensor, so a
+# recycled address can never match) together with the tensor's version counter and address, so any
+# in-place write, view, clone or copy simply misses and normalize_feature runs its own reduction.
+# Callers that want no implicit state use ``forward_with_minmax`` / ``normalize_feature(y, minmax=keys)``.
+_minmax_registry = {}
+
+
+def remember_minmax(y, keys):
+    key = id(y)
+
+    def forget(_ref, key=key):
+        _minmax_registry.pop(key, None)
+
+    _minmax_registry[key] = (weakref.ref(y, forget), keys, y._version, y.data_ptr(), tuple(y.shape))
+
+
+def recall_minmax(y):
+    entry = _minmax_registry.get(id(y))
+    if entry is None:
+        return None
+    ref, keys, version, ptr, shape = entry
+    if ref() is not y or y._version != version or y.data_ptr() != ptr or tuple(y.shape) != shape or not y.is_contiguous():
+        return None
+    return keys
 
 
 def _i32_array(values):
@@ -169,18 +199,19 @@ class LctFunction(torch.autograd.Function):
 
 class NormalizeFeatureFunction(torch.autograd.Function):
     """feature_propagation.py:260-286 on the CUDA library: ``(x - min) / (max(x - min) + 1e-15) * scale`` per
-    (batch, channel) volume, forward and backward.  ``hint`` = (keys, version, data_ptr) left on the LCT output
-    by the layer when its last kernel already reduced min / max; otherwise one reduction pass finds them."""
+    (batch, channel) volume, forward and backward.  ``keys`` = the per-channel min / max keys of exactly this
+    tensor when the LCT's last kernel already reduced them; ``None`` makes one reduction pass find them."""
 
     @staticmethod
-    def forward(ctx, x, scale, hint):
+    def forward(ctx, x, scale, keys):
         lib = _native.load()
         b, c = x.shape[0], x.shape[1]
         elems = x.numel() // (b * c)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         with torch.cuda.device(x.device):
-            if hint is not None and hint[1] == x._version and hint[2] == x.data_ptr() and hint[0].shape[0] == b * c:
-                keys = hint[0]
+            if keys is not None:
+                if keys.shape != (b * c, 2) or keys.dtype != torch.int64 or keys.device != x.device:
+                    raise ValueError("minmax keys must be the (B*D, 2) int64 tensor forward_with_minmax returned")
             else:
                 keys = torch.empty((b * c, 2), dtype=torch.int64, device=x.device)
                 _native.check(lib.lct_minmax(x.data_ptr(), b * c, elems, keys.data_ptr(), stream))

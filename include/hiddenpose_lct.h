@@ -23,10 +23,16 @@
  * Plain C types only: pointers, sizes, integer return codes (0 = success).  Nothing
  * throws across this boundary.  Device pointers are raw CUDA device addresses; `stream`
  * is a cudaStream_t passed as void*.  The caller owns all data buffers and the
- * workspace; a plan owns only immutable device constants, so one plan may be shared by
- * threads and streams as long as concurrent calls use distinct workspaces.
- * Calls are asynchronous on `stream`; they never allocate or synchronise
- * (lct_forward_host is the exception and says so).
+ * workspace; a plan owns only immutable device constants plus a few internal side streams,
+ * so one plan may be shared by threads and streams as long as concurrent calls use distinct
+ * workspaces.  The channel groups of one call run on side streams that belong to the caller's
+ * stream (four sets per plan, handed out per distinct caller stream; callers beyond four share
+ * sets, which stays correct but orders the sharers' kernels after one another).
+ * Calls are asynchronous on `stream`; they never allocate, synchronise or read host memory
+ * after returning (lct_forward_host is the exception and says so), so they may be captured in
+ * a CUDA graph -- per-sample windows included: the window table travels as kernel parameters.
+ * If a call fails after some of its kernels were queued, everything it queued on internal
+ * streams is ordered before the caller's stream again before the error code is returned.
  */
 #ifndef HIDDENPOSE_LCT_H_
 #define HIDDENPOSE_LCT_H_

@@ -206,6 +206,22 @@ class LctOracle:
         return g
 
 
+def display_views(volume_mxnxn):
+    """The display tail of the reference's NumPy path, /root/reference/utils/lct.py:62-82, on an
+    un-clamped (M, N, N) volume: clamp below zero (:62), keep the first ``M * 100 // 128`` depth
+    bins (:64-65), divide by the maximum (:66), then the three maximum projections, each divided
+    by its own maximum as passed to ``cv2.imshow`` (:68-69 front, :78-79 left, :82-83 top)."""
+    v = np.array(volume_mxnxn, dtype=np.float32, copy=True)
+    v[v < 0] = 0
+    v = v[: v.shape[0] * 100 // 128]
+    v = v / np.max(v)
+    out = {}
+    for name, axis in (("front", 0), ("left", 1), ("top", 2)):
+        view = np.max(v, axis=axis)
+        out[name] = view / np.max(view)
+    return out
+
+
 def rel_l2(a, b):
     """Relative L2 error of ``a`` against ``b`` (the parity metric; outputs
     are O(1e-6) in magnitude so absolute tolerances are meaningless)."""

@@ -12,6 +12,12 @@ def case_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "m*.npz")))
 
 
+def case_shape(name):
+    """(M, N) of a fixture without regenerating its inputs."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    return int(z["M"]), int(z["N"])
+
+
 def make_input(seed, shape):
     return np.random.RandomState(seed).rand(*shape).astype(np.float32)
 
@@ -58,3 +64,12 @@ class Case:
 
 def constants():
     return np.load(os.path.join(GOLDEN_DIR, "constants.npz"))
+
+
+def numpy_lct_fixture():
+    """Outputs of /root/reference/utils/lct.py::lct itself (SURVEY row a19), minted by
+    tests/golden/make_golden_numpy_lct.py; the (H, W, T) measurement is regenerated from the seed."""
+    z = np.load(os.path.join(GOLDEN_DIR, "numpy_lct_m128n32.npz"))
+    N, M = int(z["N"]), int(z["M"])
+    meas = np.random.RandomState(int(z["seed"])).rand(N, N, M).astype(np.float32)
+    return z, meas

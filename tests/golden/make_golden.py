@@ -83,6 +83,13 @@ CASES = [
     ("m256n64_full",     64, 256, 1, 1,  0, 256, "lct", "diffuse",  False),   # BASELINE config 1/2 shape
     ("m32n256_window",  256,  32, 1, 1,  2,  29, "lct", "diffuse",  False),   # 512-point spatial lines: the parity-split K2/K3/K4
     ("m512n16_window",   16, 512, 1, 2,  5, 500, "lct", "diffuse",  False),   # 512 time bins: the 32-wide time kernels
+    # round 2: every remaining BASELINE shape and every compiled (M, N) the CPU oracle is too slow for in a test
+    ("m512n128_full",   128, 512, 1, 1,  0, 512, "lct", "diffuse",  False),   # BASELINE config 3 unit (512x128x128)
+    ("m512n256_full",   256, 512, 1, 1,  0, 512, "lct", "diffuse",  False),   # BASELINE config 5 (512x256x256; 14 GB on the CPU)
+    ("m256n128_window", 128, 256, 1, 1,  3, 250, "lct", "diffuse",  False),   # mid shape, partial window
+    ("m64n256_full",    256,  64, 1, 1,  0,  64, "lct", "diffuse",  False),
+    ("m128n256_window", 256, 128, 1, 1,  1, 127, "lct", "diffuse",  False),   # reference class verbatim (crop 128)
+    ("m256n256_full",   256, 256, 1, 1,  0, 256, "lct", "diffuse",  False),
 ]
 
 

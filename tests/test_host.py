@@ -197,3 +197,18 @@ def test_operator_structure_is_validated():
     plan.csr = (rp2, ci2, v2)
     with pytest.raises(AssertionError):
         plan.run(x, 1, 32, [0])                               # lct_emu_run returns 100 when build_tables refuses
+
+
+def test_layer_state_pickles_without_the_native_plan():
+    """torch.save(model) / copy.deepcopy(model) (train.py:223, EMA copies): the layer's state carries host constants
+    only; the device plan is rebuilt on first use (the CUDA half of this is in test_gpu_parity.py)."""
+    import copy
+    import pickle
+    import hiddenpose_b200 as hp
+    layer = hp.lct(spatial=8, crop=32, bin_len=0.16)
+    layer._plan = object()                      # stand-in for a live native handle: must not travel
+    for clone in (copy.deepcopy(layer), pickle.loads(pickle.dumps(layer))):
+        assert clone._plan is None and clone._M == 32 and clone._N == 8
+        assert np.array_equal(clone._csr[2], layer._csr[2])
+        assert dict(clone.state_dict()) == {}
+    layer._plan = None
