@@ -34,6 +34,41 @@ def bind_host_to_gpu(device_index: int) -> bool:
         return False
 
 
+def host_topology(device_index: int) -> dict:
+    """Where this GPU hangs off the host, as far as the box tells: NUMA nodes online, the GPU's PCI address, the NUMA
+    node sysfs and NVML report for it, and the CPUs NVML calls local.  Used by bench.py to explain the end-to-end
+    (host-link-bound) numbers at N > 1; every field is best effort (None when the box hides it)."""
+    info = {"numa_nodes_online": None, "pci_bus_id": None, "pci_numa_node": None, "nvml_cpu_affinity": None,
+            "process_cpus": None, "host_cpus": None}
+    try:
+        import os
+        info["host_cpus"] = os.cpu_count()
+        info["process_cpus"] = len(os.sched_getaffinity(0))
+        with open("/sys/devices/system/node/online") as f:
+            info["numa_nodes_online"] = f.read().strip()
+    except Exception:
+        pass
+    try:
+        import math
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        bus = pynvml.nvmlDeviceGetPciInfo(handle).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        info["pci_bus_id"] = bus
+        words = math.ceil((os.cpu_count() or 1) / 64)
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = sorted(64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1)
+        info["nvml_cpu_affinity"] = f"{cpus[0]}-{cpus[-1]} ({len(cpus)} cpus)" if cpus else None
+        short = bus.lower()[-12:]                       # sysfs uses the 4-digit domain form
+        with open(f"/sys/bus/pci/devices/{short}/numa_node") as f:
+            info["pci_numa_node"] = int(f.read().strip())
+    except Exception:
+        pass
+    return info
+
+
 class LctStreamer:
     """Pipelines ``(x_host) -> layer -> (y_host)`` over pinned host buffers.
 
