@@ -2,6 +2,7 @@
 // Host side only: plan construction, workspace carving, kernel launches.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -84,6 +85,7 @@ struct GpuLauncher {
     cudaError_t err = cudaSuccess;
     void* const* events = nullptr;          // optional: 6 cudaEvent_t recorded around the stages
     int prefetch_ahead = 0;                 // SM count when the time kernels should warm L2 for later blocks, else 0
+    int stagger_ns = 0, sms = 0;
     void mark(int i) {
         if (events && err == cudaSuccess) err = cudaEventRecord((cudaEvent_t)events[i], stream);
     }
@@ -102,6 +104,8 @@ struct GpuLauncher {
         }
         lct::Params q = p;
         q.ahead = prefetch_ahead > 0 ? prefetch_ahead * K::kMinBlocks : 0;      // resident blocks of this kernel
+        q.stagger_ns = K::kMinBlocks == 2 ? stagger_ns : 0;
+        q.sms = sms;
         int gx, gy;
         K::grid(q, gx, gy);
         kern<<<dim3(gx, gy), K::kThreads, K::kSmem, stream>>>(q, K::iterations(q));
@@ -136,7 +140,7 @@ __global__ void scale_filter_kernel(float2* f, size_t n, float s) {
 
 // Builds the scaled filter on the device from the PSF support (lct_filter_build.cuh).
 template <int N>
-int build_filter_on_device(const lct_desc* d, float2* out, bool fused, float scale) {
+int build_filter_on_device(const lct_desc* d, float2* out, int layout, float scale) {
     using PH = typename lct::ColPlan<2 * N>::type;
     using PL = typename lct::LinePlan<2 * N>::type;
     constexpr int L = 2 * N, CT = (L >= 512) ? 16 : (L < 32 ? L : 32), RB = lct::LineRows<N>::RB;
@@ -164,8 +168,9 @@ int build_filter_on_device(const lct_desc* d, float2* out, bool fused, float sca
         constexpr int RS = L + PL::R0 + ((PL::TL < 16) ? 8 : 0);
         constexpr size_t smem = (size_t)RB * RS * sizeof(float2);
         if (smem > 48 * 1024) LCT_TRYC(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        lct::FilterBuildParams fp{M, N, planes, out, fused ? 1 : 0, 1.0f / d->snr, scale, d->method_bp};
-        kern<<<dim3(L / RB, M + 1), PL::TL * RB, smem>>>(fp);
+        lct::FilterBuildParams fp{M, N, planes, out, layout, 1.0f / d->snr, scale, d->method_bp};
+        // the quarter layout only keeps rows kh <= N: the blocks above them have nothing to write
+        kern<<<dim3(layout >= 2 ? N / RB + 1 : L / RB, M + 1), PL::TL * RB, smem>>>(fp);
     }
     LCT_TRYC(cudaGetLastError());
     LCT_TRYC(cudaDeviceSynchronize());
@@ -178,8 +183,9 @@ struct DeviceBand {
     float4* ell = nullptr;
     int* rowptr = nullptr;
     float* vals = nullptr;
-    lct::BandTable view() const { return lct::BandTable{ell, rowptr, vals}; }
-    void release() { cudaFree(ell); cudaFree(rowptr); cudaFree(vals); ell = nullptr; rowptr = nullptr; vals = nullptr; }
+    float4* pair = nullptr;            // mtx tables only (the time-forward kernel's pair records)
+    lct::BandTable view() const { return lct::BandTable{ell, rowptr, vals, pair}; }
+    void release() { cudaFree(ell); cudaFree(rowptr); cudaFree(vals); cudaFree(pair); ell = nullptr; rowptr = nullptr; vals = nullptr; pair = nullptr; }
 };
 
 struct lct_plan {
@@ -190,6 +196,7 @@ struct lct_plan {
     static constexpr int kMaxGroups = 8;
     int groups = 1;
     int prefetch_ahead = 0;                 // SM count, or 0 when LCT_L2_PREFETCH=0 (see GpuLauncher::prefetch_ahead)
+    int stagger_ns = 0, sms = 0;
     // One set of side streams + fork/join events per caller stream (created up front, handed out first come first
     // served): two threads driving the plan on two streams get two sets, so neither waits on the other's kernels.
     // More distinct caller streams than sets share sets round robin -- still correct (every use is ordered by its
@@ -213,22 +220,70 @@ struct lct_plan {
         next_set = (next_set + 1) % kSideSets;
         return s;
     }
-    float2* filt = nullptr;         // natural layout (unfused K3), or
+    float2* filt = nullptr;         // natural layout (unfused K3) or, with filt_sym, its quarter (M+1, N+1, N+1); or
     float2* filt_plane = nullptr;   // [kt][kw][plane row] (plane-fused kernel); exactly one of the two is set
+    int filt_sym = 0;               // lct::FilterLayout of `filt`
     bool fused() const { return filt_plane != nullptr; }
     // S1 (C, M+1, N, N) c64, plus S2 (C, M+1, 2N, N) c64 when the middle stages are not fused
     size_t per_channel_bytes() const { return (size_t)(M + 1) * N * N * sizeof(float2) * (fused() ? 1 : 3); }
     lct::ChainTables tables() const {
-        return lct::ChainTables{mtx_falloff.view(), mtx.view(), mtxi.view(), mtxi_falloff.view(), filt, filt_plane};
+        return lct::ChainTables{mtx_falloff.view(), mtx.view(), mtxi.view(), mtxi_falloff.view(), filt, filt_plane, filt_sym};
     }
 };
 
 namespace {
+// The PSF support is mirror-symmetric in y and x about the half-sample centre (after the roll of helper.py:115-116:
+// voxel (z, y, x) <-> (z, -1-y mod 2N, x) and (z, y, -1-x mod 2N)) -- checked, not assumed: the quarter filter
+// layout is only valid then.
+bool psf_support_is_mirror_symmetric(const lct_desc* d) {
+    const int L = 2 * d->spatial;
+    std::vector<long long> keys((size_t)d->psf_count);
+    for (int i = 0; i < d->psf_count; ++i) keys[i] = (long long)d->psf_z[i] * L * L + d->psf_yx[i];
+    std::sort(keys.begin(), keys.end());
+    for (int i = 0; i < d->psf_count; ++i) {
+        const int y = d->psf_yx[i] / L, x = d->psf_yx[i] % L;
+        const long long my = (long long)d->psf_z[i] * L * L + (long long)((L - 1 - y) % L) * L + x;
+        const long long mx = (long long)d->psf_z[i] * L * L + (long long)y * L + (L - 1 - x) % L;
+        if (!std::binary_search(keys.begin(), keys.end(), my) || !std::binary_search(keys.begin(), keys.end(), mx)) return false;
+    }
+    return true;
+}
+// Same property for a caller-supplied half spectrum: W(kh) = w^kh W(2N - kh), W(kw) = w^kw W(2N - kw), to 1e-5 of
+// the largest entry (a host-built filter carries the rounding of its own FFT).
+bool host_filter_is_mirror_symmetric(const float2* f, int M, int N) {
+    const int L = 2 * N;
+    double big = 0.0;
+    const size_t n = (size_t)(M + 1) * L * L;
+    for (size_t i = 0; i < n; ++i) big = std::max(big, std::max(std::fabs((double)f[i].x), std::fabs((double)f[i].y)));
+    const double tol = 1e-5 * big;
+    std::vector<double> c(L), sn(L);
+    for (int k = 0; k < L; ++k) { c[k] = std::cos(-2.0 * M_PI * k / L); sn[k] = std::sin(-2.0 * M_PI * k / L); }
+    for (int kt = 0; kt <= M; ++kt)
+        for (int kh = 0; kh < L; ++kh)
+            for (int kw = 0; kw < L; ++kw) {
+                const float2 v = f[((size_t)kt * L + kh) * L + kw];
+                if (kh > N) {
+                    const float2 u = f[((size_t)kt * L + (L - kh)) * L + kw];
+                    if (std::fabs(u.x * c[kh] - u.y * sn[kh] - v.x) > tol || std::fabs(u.x * sn[kh] + u.y * c[kh] - v.y) > tol) return false;
+                }
+                if (kw > N) {
+                    const float2 u = f[((size_t)kt * L + kh) * L + (L - kw)];
+                    if (std::fabs(u.x * c[kw] - u.y * sn[kw] - v.x) > tol || std::fabs(u.x * sn[kw] + u.y * c[kw] - v.y) > tol) return false;
+                }
+            }
+    return true;
+}
+
 int upload_band(const std::vector<lct::EllRow>& ell, const std::vector<int32_t>& rowptr, const std::vector<float>& vals,
-                DeviceBand& out) {
+                DeviceBand& out, const std::vector<lct::PairRow>* pairs = nullptr) {
     static_assert(sizeof(lct::EllRow) == sizeof(float4), "EllRow must be 16 bytes");
+    static_assert(sizeof(lct::PairRow) == 2 * sizeof(float4), "PairRow must be 32 bytes");
     int rc = to_device(reinterpret_cast<const float4*>(ell.data()), ell.size(), &out.ell);
     if (rc) return rc;
+    if (pairs) {
+        rc = to_device(reinterpret_cast<const float4*>(pairs->data()), pairs->size() * 2, &out.pair);
+        if (rc) return rc;
+    }
     rc = to_device(rowptr.data(), rowptr.size(), &out.rowptr);
     if (rc) return rc;
     return to_device(vals.data(), vals.size(), &out.vals);
@@ -286,7 +341,7 @@ int lct_plan_create(const lct_desc* d, lct_plan** out) {
 
     // validate the operator and derive the banded row tables for mtx and mtxi = mtx^T (helper.py:61)
     lct::HostTables ht;
-    const std::string why = lct::build_tables(M, d->mtx_rowptr, d->mtx_colidx, d->mtx_vals, d->falloff, lct::time_tail_rows(M), ht);
+    const std::string why = lct::build_tables(M, d->mtx_rowptr, d->mtx_colidx, d->mtx_vals, d->falloff, lct::time_tail_rows(M), ht, lct::time_long_pairs(M));
     if (!why.empty()) return fail(LCT_ERR_INVALID, why.c_str());
 
     lct_plan* p = new (std::nothrow) lct_plan();
@@ -294,25 +349,41 @@ int lct_plan_create(const lct_desc* d, lct_plan** out) {
     p->M = M; p->N = N; p->device = d->device;
     const size_t nfilt = (size_t)(M + 1) * 4 * N * N;
 #define LCT_TRY(expr) do { rc = (expr); if (rc) { lct_plan_destroy(p); return rc; } } while (0)
-    LCT_TRY(upload_band(ht.mtx_ell_falloff, ht.mtx_rowptr, ht.mtx_vals_falloff, p->mtx_falloff));
-    LCT_TRY(upload_band(ht.mtx_ell, ht.mtx_rowptr, ht.mtx_vals, p->mtx));
+    LCT_TRY(upload_band(ht.mtx_ell_falloff, ht.mtx_rowptr, ht.mtx_vals_falloff, p->mtx_falloff, &ht.mtx_pair_falloff));
+    LCT_TRY(upload_band(ht.mtx_ell, ht.mtx_rowptr, ht.mtx_vals, p->mtx, &ht.mtx_pair));
     LCT_TRY(upload_band(ht.mtxi_ell, ht.mtxi_rowptr, ht.mtxi_vals, p->mtxi));
     LCT_TRY(upload_band(ht.mtxi_ell_falloff, ht.mtxi_rowptr, ht.mtxi_vals_falloff, p->mtxi_falloff));
     // fold torch.ifft's 1/(2M*2N*2N) (tflct.py:151) into the filter; a power of two, so exact
     const float scale = 1.0f / (8.0f * (float)M * (float)N * (float)N);
     const bool fused = lct::plane_fusable(N) && !(d->reserved & LCT_FLAG_NO_PLANE_FUSION);
     float2** slot = fused ? &p->filt_plane : &p->filt;
+    const bool allow_sym = !fused && !(d->reserved & LCT_FLAG_FULL_FILTER);
+    // which part of a symmetric filter the unfused column kernel of this size wants (lct_kernels.cuh, Params::filt_sym)
+    const int sym_layout = N >= 256 ? lct::kFilterHalfRows : lct::kFilterQuarter;
+    const int sym_pitch = sym_layout == lct::kFilterHalfRows ? 2 * N : N + 1;
+    const size_t nquarter = (size_t)(M + 1) * (N + 1) * sym_pitch;
     if (device_filter) {
-        cudaError_t e = cudaMalloc((void**)slot, nfilt * sizeof(float2));
-        if (e != cudaSuccess) { lct_plan_destroy(p); return fail(LCT_ERR_NOMEM, "filter allocation", e); }
         for (int i = 0; i < d->psf_count; ++i)
             if (d->psf_z[i] < 0 || d->psf_z[i] >= 2 * M || d->psf_yx[i] < 0 || d->psf_yx[i] >= 4 * N * N) {
                 lct_plan_destroy(p);
                 return fail(LCT_ERR_INVALID, "PSF voxel out of range");
             }
+        p->filt_sym = (allow_sym && psf_support_is_mirror_symmetric(d)) ? sym_layout : lct::kFilterFull;
+        cudaError_t e = cudaMalloc((void**)slot, (p->filt_sym ? nquarter : nfilt) * sizeof(float2));
+        if (e != cudaSuccess) { lct_plan_destroy(p); return fail(LCT_ERR_NOMEM, "filter allocation", e); }
         rc = -1;
-        LCT_SWITCH_N(N, (build_filter_on_device<kN>(d, *slot, fused, scale)));
+        LCT_SWITCH_N(N, (build_filter_on_device<kN>(d, *slot, fused ? 1 : (p->filt_sym == lct::kFilterQuarter ? 2 : (p->filt_sym == lct::kFilterHalfRows ? 3 : 0)), scale)));
         if (rc) { lct_plan_destroy(p); return rc < 0 ? fail(LCT_ERR_UNSUPPORTED, "size not compiled") : rc; }
+    } else if (allow_sym && host_filter_is_mirror_symmetric(reinterpret_cast<const float2*>(d->filter_half), M, N)) {
+        const int L = 2 * N;
+        const float2* nat = reinterpret_cast<const float2*>(d->filter_half);
+        std::vector<float2> quarter(nquarter);
+        for (int kt = 0; kt <= M; ++kt)
+            for (int kh = 0; kh <= N; ++kh)
+                std::memcpy(&quarter[((size_t)kt * (N + 1) + kh) * sym_pitch], &nat[((size_t)kt * L + kh) * L], sizeof(float2) * sym_pitch);
+        LCT_TRY(to_device(quarter.data(), nquarter, slot));
+        p->filt_sym = sym_layout;
+        scale_filter_kernel<<<1024, 256>>>(*slot, nquarter, scale);
     } else {
         if (fused) {
             // fused layout: [kt][kw/2][plane row][kw&1] -- both output parities of a row in one 128-bit load,
@@ -342,6 +413,9 @@ int lct_plan_create(const lct_desc* d, lct_plan** out) {
         int sms = 0;
         if ((!pf || std::atoi(pf) != 0) && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->device) == cudaSuccess)
             p->prefetch_ahead = sms;
+        cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, d->device);
+        const char* sg = std::getenv("LCT_STAGGER_NS");
+        p->stagger_ns = sg ? std::atoi(sg) : 0;
     }
     {
         const char* env = std::getenv("LCT_STREAM_GROUPS");
@@ -438,6 +512,7 @@ static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const 
             }
             GpuLauncher lg{sg, plan->device};
             lg.prefetch_ahead = plan->prefetch_ahead;
+            lg.stagger_ns = plan->stagger_ns; lg.sms = plan->sms;
             const int rc = lct::run_chain(lg, t, M, N, (int)(c1 - c0), D, Tin, tbe[0], be_dev, (int)c0,
                                           in + (size_t)c0 * in_stride, out + (size_t)c0 * out_stride,
                                           s1 + (size_t)c0 * (M + 1) * N * N, s2 + (size_t)c0 * (M + 1) * 2 * N * N, backward,
@@ -458,6 +533,7 @@ static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const 
     GpuLauncher l{stream, plan->device};
     l.events = events;
     l.prefetch_ahead = plan->prefetch_ahead;
+    l.stagger_ns = plan->stagger_ns; l.sms = plan->sms;
     for (long long c0 = 0; c0 < C; c0 += chunk) {
         const int cn = (int)((C - c0 < chunk) ? (C - c0) : chunk);
         const int rc = lct::run_chain(l, t, M, N, cn, D, Tin, tbe[0], be_dev, (int)c0,

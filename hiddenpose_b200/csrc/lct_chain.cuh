@@ -98,10 +98,13 @@ template <int N, class Launcher> int launch_col_filter(const Params& p, Launcher
     // (The two parities side by side in one warp, as the H-axis kernels do it, measured slower here: 673-795 vs 560 us.)
     if constexpr (N >= 256) {
         using PL = typename LinePlan<N>::type;
-        return l.template launch<ColFilterSplit<PL, 256 / PL::TL>>(p);
+        if (p.filt_sym) return l.template launch<ColFilterSplit<PL, 256 / PL::TL, true>>(p);
+        return l.template launch<ColFilterSplit<PL, 256 / PL::TL, false>>(p);
     }
-    else
-        return l.template launch<ColFilter<typename LinePlan<2 * N>::type, LineRows<N>::RB>>(p);
+    else {
+        if (p.filt_sym) return l.template launch<ColFilter<typename LinePlan<2 * N>::type, LineRows<N>::RB, true>>(p);
+        return l.template launch<ColFilter<typename LinePlan<2 * N>::type, LineRows<N>::RB, false>>(p);
+    }
 }
 template <int N, class Launcher> int launch_plane(const Params& p, Launcher& l) {
     if constexpr (plane_fusable(N)) return l.template launch<typename PlaneKernel<N>::type>(p);
@@ -136,16 +139,24 @@ inline int time_tail_rows(int M) {
     LCT_SWITCH_M(M, (time_tail_rows_for<kM>()));
     return rc < 0 ? 0 : rc;
 }
+// Pairs (2p, 2p+1) of mtx rows from this index on are applied through pair records (at most three columns together).
+template <int M> constexpr int time_long_pairs_for() { return TimeLongQ<M>::Q * TimeFwdPlan<M>::type::st(0); }
+inline int time_long_pairs(int M) {
+    int rc = 0;
+    LCT_SWITCH_M(M, (time_long_pairs_for<kM>()));
+    return rc < 0 ? 0 : rc;
+}
 
 // Resampling-operator tables the chain needs (device pointers on the GPU; see lct_tables.h).
-struct BandTable { const float4* ell; const int* rowptr; const float* vals; };
+struct BandTable { const float4* ell; const int* rowptr; const float* vals; const float4* pair; };
 struct ChainTables {
     BandTable mtx_falloff;      // mtx[i][j] * falloff[j]     forward  K1
     BandTable mtx;              // mtx[i][j]                  backward K1
     BandTable mtxi;             // mtxi[j][i]                 forward  K5
     BandTable mtxi_falloff;     // mtxi[j][i] * falloff[j]    backward K5
-    const float2* filt;         // (M+1, 2N, 2N) natural order, for K3            (null if fused)
+    const float2* filt;         // (M+1, 2N, 2N) natural order -- or its (M+1, N+1, N+1) quarter -- for K3 (null if fused)
     const float2* filt_plane;   // (M+1, 2N kw, 2N plane rows), for PlaneFilter   (null if not fused)
+    int filt_sym;               // FilterLayout of filt (Params::filt_sym)
 };
 
 // Runs the stages selected in `mask` (all five for a real call).
@@ -159,7 +170,7 @@ int run_chain(Launcher& l, const ChainTables& t, int M, int N, int C, int D, int
               unsigned long long* minmax_keys = nullptr) {
     Params p{};
     p.M = M; p.N = N; p.C = C; p.D = D;
-    p.s1 = s1; p.s2 = s2; p.filt = t.filt; p.conj_filter = backward ? 1 : 0;
+    p.s1 = s1; p.s2 = s2; p.filt = t.filt; p.conj_filter = backward ? 1 : 0; p.filt_sym = t.filt_sym;
     p.in = in; p.out = out; p.c_base = c_base;
     int rc = 0;
     l.mark(0);
@@ -168,7 +179,7 @@ int run_chain(Launcher& l, const ChainTables& t, int M, int N, int C, int D, int
         p.be_uniform = backward ? 0 : be_uniform;
         p.be_dev = backward ? nullptr : be_dev;
         const BandTable& bt = backward ? t.mtx : t.mtx_falloff;
-        p.ell = bt.ell; p.rowptr = bt.rowptr; p.vals = bt.vals;
+        p.ell = bt.ell; p.rowptr = bt.rowptr; p.vals = bt.vals; p.pair = bt.pair;
         LCT_SWITCH_M(M, (launch_time_fwd<kM>(p, l)));
         if (rc) return rc;
     }

@@ -20,7 +20,7 @@ struct FilterBuildParams {
     int M, N;                      // L = 2N
     float2* planes;                // (M+1, L, L) scratch, natural order
     float2* out;                   // final filter
-    int fused_layout;              // 1: [kt][kw/2][plane row][kw&1]   0: [kt][kh][kw]
+    int fused_layout;              // 1: [kt][kw/2][plane row][kw&1]   0: [kt][kh][kw]   2: quarter [kt][kh <= N][kw <= N]   3: half rows [kt][kh <= N][kw]
     float inv_snr, scale;
     int conj_only;                 // method == 'bp'
 };
@@ -92,6 +92,14 @@ row_fft_wiener_kernel(FilterBuildParams p) {
             }
             w.x *= p.scale;
             w.y *= p.scale;
+            if (p.fused_layout == 2) {
+                if (kh <= N && kw <= N) p.out[((size_t)kt * (N + 1) + kh) * (N + 1) + kw] = w;
+                return;
+            }
+            if (p.fused_layout == 3) {
+                if (kh <= N) p.out[((size_t)kt * (N + 1) + kh) * L + kw] = w;
+                return;
+            }
             const size_t o = p.fused_layout ? ((((size_t)kt * N + (kw >> 1)) * L + plane_row) * 2 + (kw & 1))
                                             : (((size_t)kt * L + kh) * L + kw);
             p.out[o] = w;

@@ -100,7 +100,9 @@ template <int L> struct TwShared {
         return reinterpret_cast<const float2*>(lct_dyn_smem)[i / (kTwN / L)];
     }
     static LCT_DEV void fill(unsigned char* smem, int tid, int nthreads) {
-        for (int j = tid; j < L; j += nthreads) reinterpret_cast<float2*>(smem)[j] = c_tw[j * (kTwN / L)];
+        // from the global copy of the table: every lane wants a different entry, which the constant bank would
+        // serialise (32 passes per warp -- 6 % of the plane kernel's time went into this fill); one coalesced load here
+        for (int j = tid; j < L; j += nthreads) reinterpret_cast<float2*>(smem)[j] = __ldg(&g_tw[j * (kTwN / L)]);
     }
 #endif
     static LCT_DEV float2 mul(float2 a, int i) { return cmul(a, get(i)); }
@@ -125,7 +127,7 @@ template <class P> struct TwLine {
     static LCT_DEV void fill(unsigned char* smem, int tid, int nthreads) {
         for (int j = tid; j < L; j += nthreads) {
             const int k = j / STR0, lo = j % STR0;
-            reinterpret_cast<float2*>(smem)[j] = c_tw[((k * lo) % L) * (kTwN / L)];
+            reinterpret_cast<float2*>(smem)[j] = __ldg(&g_tw[((k * lo) % L) * (kTwN / L)]);   // lane-divergent: not the constant bank
         }
     }
 #endif
@@ -171,20 +173,33 @@ struct Params {
     float* out;
     float2* s1;                 // (C, M+1, N, N)
     float2* s2;                 // (C, M+1, 2N, N)
-    const float2* filt;         // (M+1, 2N, 2N), already scaled by 1/(8 M N N)
+    const float2* filt;         // (M+1, 2N, 2N), already scaled by 1/(8 M N N); or its quarter (filt_sym)
     int conj_filter;
+    // filt_sym: only part of the filter is stored.  The light-cone PSF is mirror-symmetric in y and in x about a
+    // half-sample centre (psf[-1-x] = psf[x] after the roll of helper.py:115-116), so along either axis
+    // W(k) = w_2N^k W(2N - k) for k > N (and W(N) = 0): the mirrored part is the stored one times a twiddle.
+    //   kFilterQuarter  (M+1, N+1, N+1): kh, kw <= N -- for the kernels that keep a filter row in registers across
+    //                   the channel loop, where the per-value twiddle is paid once per block;
+    //   kFilterHalfRows (M+1, N+1, 2N):  kh <= N     -- for the 512-point kernel, which re-reads the filter per
+    //                   channel: one row-constant twiddle, no per-value table lookup.
+    // lct_plan_create verifies the symmetry before choosing either layout.
+    int filt_sym;
     // Resampling operator used by this launch (mtx rows for K1, mtxi rows for K5): one 16-byte
     // record per row {start * kEllStride, w0, w1, w2} (lct_tables.h); rows longer than 3
     // continue in vals[rowptr[row] + 3 ...].
     const float4* ell;
     const int* rowptr;
     const float* vals;
+    const float4* pair;         // K1 only: pair records (two float4 per pair, lct_tables.h); pairs below kLongPairs unused
     // optional (K5, forward): per-channel {min key, complemented max key} of the volume it writes, reduced
     // with atomicMin while the values are still in registers (lct_normalize.cuh); pre-set to all ones
     unsigned long long* minmax_keys;
     // time kernels: how many blocks ahead (in launch order) the tile to warm in L2 lies; 0 = no prefetch.
     // The launcher sets it to the number of resident blocks, so the lines arrive about one block life early.
     int ahead;
+    // experiment hook (LCT_STAGGER_NS): blocks of the second residency slot of each SM start this many ns late, so
+    // that co-resident blocks run their memory and compute phases out of step; sms = SM count
+    int stagger_ns, sms;
 };
 
 LCT_DEV void prefetch_l2(const void* ptr) {
@@ -272,23 +287,38 @@ LCT_DEV void minmax_commit(unsigned long long* keys, int c, unsigned long long k
 template <bool kTail>
 LCT_DEV float band_dot(const Params& p, const float4* ell, int row, const float* src) {
     const float4 e = ell[row];                     // block-local copy in shared memory (warp-uniform: broadcast)
-    const float* s = src + float_bits(e.x);
+    // the low bits of the offset hold the number of entries past the third; they are zero wherever kTail is false
+    const int off = float_bits(e.x), extra = kTail ? (off & (kEllStride - 1)) : 0;
+    const float* s = src + (off - extra);
     float acc = e.y * s[0];
     acc = fmaf(e.z, s[kEllStride], acc);
     acc = fmaf(e.w, s[2 * kEllStride], acc);
     if constexpr (kTail) {
-        const int first = LCT_LDG(p.rowptr + row), len = LCT_LDG(p.rowptr + row + 1) - first;
-        if (len > 3) {
-            const float* v = p.vals + first;
-            for (int k = 3; k < len; ++k) acc = fmaf(LCT_LDG(v + k), s[k * kEllStride], acc);
+        if (extra) {                               // rare (the first ~sqrt(M)/6 rows of mtx): the CSR arrays hold the rest
+            const float* v = p.vals + LCT_LDG(p.rowptr + row);
+            for (int k = 3; k < 3 + extra; ++k) acc = fmaf(LCT_LDG(v + k), s[k * kEllStride], acc);
         }
     }
     return acc;
 }
 
+// Rows (2 pair, 2 pair + 1) of the operator applied together through one pair record (lct_tables.h): three tile
+// loads, six multiply-adds.  Only valid for pairs >= kLongPairs (build_tables checks the operator).
+LCT_DEV float2 pair_dot(const float4* pairs, int pair, const float* src) {
+    const float4 a = pairs[2 * pair], b = pairs[2 * pair + 1];       // {offset, a0, a1, a2}, {b0, b1, b2, -}
+    const float* s = src + float_bits(a.x);
+    const float x0 = s[0], x1 = s[kEllStride], x2 = s[2 * kEllStride];
+    return make_float2(fmaf(a.w, x2, fmaf(a.z, x1, a.y * x0)), fmaf(b.z, x2, fmaf(b.y, x1, b.x * x0)));
+}
+
 LCT_DEV int window_begin(const Params& p, int c) {
     return p.be_dev ? LCT_LDG(p.be_dev + (p.c_base + c) / p.D) : p.be_uniform;
 }
+
+// Stage-0 butterfly inputs q < Q of the time-forward kernel cover the pairs whose two rows may span more than three
+// columns together (pairs up to ~M/10 of helper.py:35-69's operator: 1 / 4 / 10 / 24 / 53 at M = 32 ... 512); the
+// rest take one pair record each.  build_tables refuses an operator that does not fit.
+template <int M> struct TimeLongQ { static constexpr int Q = (M >= 512) ? 4 : ((M >= 128) ? 2 : 1); };
 
 // ---------------------------------------------------------------------------
 // K1: time window + falloff + resample + real FFT (2M, M non-zero) along T.
@@ -305,7 +335,11 @@ template <class P, int CT_> struct TimeFwd {
     // the kernel at two blocks per SM, so nothing is gained by aliasing them (and a phase is saved)
     static constexpr size_t kXs = ((size_t)(M + 2) * CT * sizeof(float) + 15) / 16 * 16;
     static constexpr size_t kWork = kXs + (size_t)M * CT * sizeof(float2);
-    static constexpr size_t kSmem = TwS::kBytes + (kWork + (size_t)M * sizeof(float4));
+    // operator tables behind the work buffers: the pair records (M/2 x 32 B) and the row records of the first
+    // kLongRows rows, the only ones still applied row by row
+    static constexpr int kLongQ = TimeLongQ<M>::Q, kLongPairs = kLongQ * P::st(0), kLongRows = 2 * kLongPairs;
+    static_assert(P::TL == P::st(0), "stage-0 butterfly q of line thread tau starts at pair tau + q * st(0)");
+    static constexpr size_t kSmem = TwS::kBytes + (kWork + (size_t)(M + kLongRows) * sizeof(float4));
     static constexpr bool kWarpSync = false;
     // 1024 threads/SM at <= 64 regs; the 32-wide butterflies need 128 regs (512 threads/SM)
     static constexpr int kMinBlocks = (P::E >= 32) ? (512 / kThreads > 0 ? 512 / kThreads : 1) : ((kThreads >= 1024) ? 1 : 1024 / kThreads);
@@ -328,7 +362,8 @@ template <class P, int CT_> struct TimeFwd {
             constexpr int V4 = CT / 4, kSlots = (M + 2) * V4;
             const float4* src = reinterpret_cast<const float4*>(p.in + (size_t)c * p.in_T * NN + col0);
             float4* xs4 = reinterpret_cast<float4*>(smem);
-            for (int j = tid; j < M; j += kThreads) reinterpret_cast<float4*>(smem + kWork)[j] = LCT_LDG(p.ell + j);
+            for (int j = tid; j < M + kLongRows; j += kThreads)
+                reinterpret_cast<float4*>(smem + kWork)[j] = j < M ? LCT_LDG(p.pair + j) : LCT_LDG(p.ell + (j - M));
             // slot i = tid + u * kThreads covers row t = i / V4, column quad q = i % V4: q is fixed per
             // thread and t advances by kThreads / V4 per slot, so the source offset is stepped, not recomputed
             static_assert(kThreads % V4 == 0, "column quad must be fixed per thread");
@@ -361,8 +396,11 @@ template <class P, int CT_> struct TimeFwd {
         } else if constexpr (PH == 1) {
             fwd_stage<P, 0, true, TwS>(tau,
                 [&](int pos, int slot) {
-                    // rows longer than three taps sit below kTailRows = 2 * st(0): first input of a butterfly only
-                    const float4* ell = reinterpret_cast<const float4*>(smem + kWork);
+                    // input q of the butterfly is pair tau + q * st(0): from q = kLongQ on, one pair record; below, row
+                    // by row -- and rows longer than three taps sit below 2 * st(0): the first input of a butterfly only
+                    const float4* pairs = reinterpret_cast<const float4*>(smem + kWork);
+                    const float4* ell = pairs + M;
+                    if (slot % P::radix(0) >= kLongQ) return pair_dot(pairs, pos, xs + col);
                     if (slot % P::radix(0) == 0)
                         return make_float2(band_dot<true>(p, ell, 2 * pos, xs + col), band_dot<true>(p, ell, 2 * pos + 1, xs + col));
                     return make_float2(band_dot<false>(p, ell, 2 * pos, xs + col), band_dot<false>(p, ell, 2 * pos + 1, xs + col));
@@ -422,7 +460,11 @@ template <class P, int CT_> struct TimeFwdPersistent {
     // the kernel at two blocks per SM, so nothing is gained by aliasing them (and a phase is saved)
     static constexpr size_t kXs = ((size_t)(M + 2) * CT * sizeof(float) + 15) / 16 * 16;
     static constexpr size_t kWork = kXs + (size_t)M * CT * sizeof(float2);
-    static constexpr size_t kSmem = TwS::kBytes + (kWork + (size_t)M * sizeof(float4));
+    // operator tables behind the work buffers: the pair records (M/2 x 32 B) and the row records of the first
+    // kLongRows rows, the only ones still applied row by row
+    static constexpr int kLongQ = TimeLongQ<M>::Q, kLongPairs = kLongQ * P::st(0), kLongRows = 2 * kLongPairs;
+    static_assert(P::TL == P::st(0), "stage-0 butterfly q of line thread tau starts at pair tau + q * st(0)");
+    static constexpr size_t kSmem = TwS::kBytes + (kWork + (size_t)(M + kLongRows) * sizeof(float4));
     static constexpr bool kWarpSync = false;
     // 1024 threads/SM at <= 64 regs; the 32-wide butterflies need 128 regs (512 threads/SM)
     static constexpr int kMinBlocks = (P::E >= 32) ? (512 / kThreads > 0 ? 512 / kThreads : 1) : ((kThreads >= 1024) ? 1 : 1024 / kThreads);
@@ -478,7 +520,8 @@ template <class P, int CT_> struct TimeFwdPersistent {
         float2* zs = reinterpret_cast<float2*>(smem + kXs);
         if constexpr (PH == 0 && kPersist) {
             if (it == 0) {
-                for (int j = tid; j < M; j += kThreads) reinterpret_cast<float4*>(smem + kWork)[j] = LCT_LDG(p.ell + j);
+                for (int j = tid; j < M + kLongRows; j += kThreads)
+                reinterpret_cast<float4*>(smem + kWork)[j] = j < M ? LCT_LDG(p.pair + j) : LCT_LDG(p.ell + (j - M));
                 issue_tile(p, smem, tid, tile);
             }
             cp_async_wait_all();                             // later tiles were issued during the previous tile's stages
@@ -488,7 +531,8 @@ template <class P, int CT_> struct TimeFwdPersistent {
             constexpr int V4 = CT / 4, kSlots = (M + 2) * V4;
             const float4* src = reinterpret_cast<const float4*>(p.in + (size_t)c * p.in_T * NN + col0);
             float4* xs4 = reinterpret_cast<float4*>(smem);
-            for (int j = tid; j < M; j += kThreads) reinterpret_cast<float4*>(smem + kWork)[j] = LCT_LDG(p.ell + j);
+            for (int j = tid; j < M + kLongRows; j += kThreads)
+                reinterpret_cast<float4*>(smem + kWork)[j] = j < M ? LCT_LDG(p.pair + j) : LCT_LDG(p.ell + (j - M));
             constexpr int kRowStep = kThreads / V4, kIters = (kSlots + kThreads - 1) / kThreads;
             const int t0 = tid / V4;
             ptrdiff_t off = (ptrdiff_t)(t0 - be) * (NN / 4) + tid % V4;
@@ -514,8 +558,11 @@ template <class P, int CT_> struct TimeFwdPersistent {
         } else if constexpr (PH == 1) {
             fwd_stage<P, 0, true, TwS>(tau,
                 [&](int pos, int slot) {
-                    // rows longer than three taps sit below kTailRows = 2 * st(0): first input of a butterfly only
-                    const float4* ell = reinterpret_cast<const float4*>(smem + kWork);
+                    // input q of the butterfly is pair tau + q * st(0): from q = kLongQ on, one pair record; below, row
+                    // by row -- and rows longer than three taps sit below 2 * st(0): the first input of a butterfly only
+                    const float4* pairs = reinterpret_cast<const float4*>(smem + kWork);
+                    const float4* ell = pairs + M;
+                    if (slot % P::radix(0) >= kLongQ) return pair_dot(pairs, pos, xs + col);
                     if (slot % P::radix(0) == 0)
                         return make_float2(band_dot<true>(p, ell, 2 * pos, xs + col), band_dot<true>(p, ell, 2 * pos + 1, xs + col));
                     return make_float2(band_dot<false>(p, ell, 2 * pos, xs + col), band_dot<false>(p, ell, 2 * pos + 1, xs + col));
@@ -923,13 +970,19 @@ template <class P, int CT_> struct RowInvSplit {
     }
 };
 
+enum FilterLayout { kFilterFull = 0, kFilterQuarter = 1, kFilterHalfRows = 2 };
+// Symmetric-filter addressing (Params::filt_sym): index of frequency k in the stored range [0, N] and the exponent
+// of the twiddle w_2N that maps the stored value onto W(k) (0 for k <= N).
+template <int N> LCT_DEV int sym_index(int k) { return k <= N ? k : 2 * N - k; }
+template <int N> LCT_DEV int sym_twist(int k) { return k <= N ? 0 : k; }
+
 // ---------------------------------------------------------------------------
 // K3: along W (the contiguous axis): zero-extended FFT, filter multiply, inverse
 // FFT, crop -- in place on S2.  One block = RB consecutive kh rows of one kt
 // plane; it loops over the channels so the filter row stays in registers.
 // Two-stage plans only (lanes run along the line so global accesses coalesce).
 // ---------------------------------------------------------------------------
-template <class P, int RB_> struct ColFilter {
+template <class P, int RB_, bool SYM = false> struct ColFilter {
     static_assert(P::S == 2, "ColFilter needs a two-stage plan");
     static_assert(32 % P::TL == 0, "the threads of one line must share a warp");
     static constexpr int L = P::L, N = L / 2, RB = RB_, kThreads = P::TL * RB;
@@ -944,6 +997,7 @@ template <class P, int RB_> struct ColFilter {
     static constexpr int RS = L + P::R0 * PAD + ((P::TL < 16) ? 8 : 0);    // row stride in float2
     static constexpr size_t kSmem = TwL::kBytes + (size_t)RB * RS * sizeof(float2);
     static constexpr int kIn = P::E / 2;                                   // non-zero inputs per thread
+    static constexpr int kFiltPitch = SYM ? N + 1 : L;                     // stored filter row, in values (kFilterQuarter)
     struct Regs { float2 w[P::E]; float2 pre[kIn]; };
     static void grid(const Params& p, int& gx, int& gy) { gx = L / RB; gy = p.M + 1; }
     static int iterations(const Params& p) { return p.C; }
@@ -977,20 +1031,43 @@ template <class P, int RB_> struct ColFilter {
                 if (next / gx <= p.M) {
                     const size_t first = (size_t)(next / gx) * L + (size_t)(next % gx) * RB;          // kt * L + kh
                     const char* rows = reinterpret_cast<const char*>(p.s2 + first * N);
-                    const char* filt = reinterpret_cast<const char*>(p.filt + first * L);
-                    constexpr int kRowLines = RB * N * (int)sizeof(float2) / 128, kFiltLines = RB * L * (int)sizeof(float2) / 128;
+                    constexpr int kRowLines = RB * N * (int)sizeof(float2) / 128;
                     for (int i = tid; i < kRowLines; i += kThreads) prefetch_l2(rows + (size_t)i * 128);
-                    for (int i = tid; i < kFiltLines; i += kThreads) prefetch_l2(filt + (size_t)i * 128);
+                    if constexpr (SYM) {
+                        // the RB stored rows this block will read: kh' descends when kh > N
+                        const int nkh = (int)(next % gx) * RB, lo = nkh < N ? nkh : 2 * N - (nkh + RB - 1);
+                        const int nrows = (lo + RB <= N + 1) ? RB : N + 1 - lo;
+                        const char* filt = reinterpret_cast<const char*>(p.filt + ((size_t)(next / gx) * (N + 1) + lo) * kFiltPitch);
+                        for (int i = tid; i < (nrows * kFiltPitch * (int)sizeof(float2) + 127) / 128; i += kThreads) prefetch_l2(filt + (size_t)i * 128);
+                    } else {
+                        const char* filt = reinterpret_cast<const char*>(p.filt + first * L);
+                        constexpr int kFiltLines = RB * L * (int)sizeof(float2) / 128;
+                        for (int i = tid; i < kFiltLines; i += kThreads) prefetch_l2(filt + (size_t)i * 128);
+                    }
                 }
             }
             if (it == 0) {
                 fetch(row, tau, r);
-                const float2* f = p.filt + ((size_t)kt * L + kh) * L;
-                for_each_slot<P, 1>(tau, [&](int pos, int slot) {
-                    float2 w = LCT_LDG(f + P::template freq_of<1>(pos, slot));
-                    if (p.conj_filter) w.y = -w.y;
-                    r.w[slot] = w;
-                });
+                if constexpr (SYM) {
+                    // quarter filter: stored row kh' = min(kh, 2N - kh), stored column kw' likewise; one twiddle
+                    // w_2N^(twist(kh) + twist(kw)) per value, paid once per block (the row stays in registers)
+                    const float2* f = p.filt + ((size_t)kt * (N + 1) + sym_index<N>(kh)) * (N + 1);
+                    const int th = sym_twist<N>(kh);
+                    for_each_slot<P, 1>(tau, [&](int pos, int slot) {
+                        const int kw = P::template freq_of<1>(pos, slot);
+                        float2 w = LCT_LDG(f + sym_index<N>(kw));
+                        w = TwGlobal::mul(w, ((th + sym_twist<N>(kw)) & (L - 1)) * (kTwN / L));
+                        if (p.conj_filter) w.y = -w.y;
+                        r.w[slot] = w;
+                    });
+                } else {
+                    const float2* f = p.filt + ((size_t)kt * L + kh) * L;
+                    for_each_slot<P, 1>(tau, [&](int pos, int slot) {
+                        float2 w = LCT_LDG(f + P::template freq_of<1>(pos, slot));
+                        if (p.conj_filter) w.y = -w.y;
+                        r.w[slot] = w;
+                    });
+                }
             }
             constexpr int r0 = P::R0;
             fwd_stage<P, 0, true, TwL>(tau,
@@ -1019,7 +1096,7 @@ template <class P, int RB_> struct ColFilter {
 // inverted, y[n] = y_even[n] + conj(w_2N^n) y_odd[n].  Same arithmetic as ColFilter, but the butterflies
 // are 16 wide instead of 32: a third of the registers and twice the resident warps.  P is the N-point plan.
 // ---------------------------------------------------------------------------
-template <class P, int RB_> struct ColFilterSplit {
+template <class P, int RB_, bool SYM = false> struct ColFilterSplit {
     static_assert(P::S == 2, "ColFilterSplit needs a two-stage plan");
     static_assert(32 % P::TL == 0, "the threads of one line must share a warp");
     static constexpr int N = P::L, L = 2 * N, RB = RB_, kThreads = P::TL * RB;
@@ -1030,6 +1107,7 @@ template <class P, int RB_> struct ColFilterSplit {
     static constexpr int PAD = 1;
     static constexpr int RS = N + P::R0 * PAD + ((P::TL < 16) ? 8 : 0);    // row stride in float2
     static constexpr size_t kSmem = TwL::kBytes + (size_t)2 * RB * RS * sizeof(float2);     // even and odd exchange rows
+    static constexpr int kFiltPitch = L;                                   // stored filter row, in values (kFilterHalfRows keeps whole rows)
     struct Regs { float2 in[P::E]; };
     static void grid(const Params& p, int& gx, int& gy) { gx = L / RB; gy = p.M + 1; }
     static int iterations(const Params& p) { return p.C; }
@@ -1057,10 +1135,19 @@ template <class P, int RB_> struct ColFilterSplit {
                 if (next / gx <= p.M) {
                     const size_t first = (size_t)(next / gx) * L + (size_t)(next % gx) * RB;          // kt * L + kh
                     const char* rows = reinterpret_cast<const char*>(p.s2 + first * N);
-                    const char* filt = reinterpret_cast<const char*>(p.filt + first * L);
-                    constexpr int kRowLines = RB * N * (int)sizeof(float2) / 128, kFiltLines = RB * L * (int)sizeof(float2) / 128;
+                    constexpr int kRowLines = RB * N * (int)sizeof(float2) / 128;
                     for (int i = tid; i < kRowLines; i += kThreads) prefetch_l2(rows + (size_t)i * 128);
-                    for (int i = tid; i < kFiltLines; i += kThreads) prefetch_l2(filt + (size_t)i * 128);
+                    if constexpr (SYM) {
+                        // the RB stored rows this block will read: kh' descends when kh > N
+                        const int nkh = (int)(next % gx) * RB, lo = nkh < N ? nkh : 2 * N - (nkh + RB - 1);
+                        const int nrows = (lo + RB <= N + 1) ? RB : N + 1 - lo;
+                        const char* filt = reinterpret_cast<const char*>(p.filt + ((size_t)(next / gx) * (N + 1) + lo) * kFiltPitch);
+                        for (int i = tid; i < (nrows * kFiltPitch * (int)sizeof(float2) + 127) / 128; i += kThreads) prefetch_l2(filt + (size_t)i * 128);
+                    } else {
+                        const char* filt = reinterpret_cast<const char*>(p.filt + first * L);
+                        constexpr int kFiltLines = RB * L * (int)sizeof(float2) / 128;
+                        for (int i = tid; i < kFiltLines; i += kThreads) prefetch_l2(filt + (size_t)i * 128);
+                    }
                 }
             }
             if (it == 0) fetch(row, tau, r);
@@ -1072,25 +1159,27 @@ template <class P, int RB_> struct ColFilterSplit {
                 [&](int pos, int, float2 v) { zo[padpos(pos)] = v; });
             if (it + 1 < p.C) fetch(row + chan, tau, r);        // next channel's row flies during this one's math
         } else if constexpr (PH == 1) {
-            // natural filter layout [kt][kh][kw]: even parity reads kw = 2f, odd parity kw = 2f + 1
-            const float2* f = p.filt + ((size_t)kt * L + kh) * L;
-            float2 w[P::E], a[P::E];
-            for_each_slot<P, 1>(tau, [&](int pos, int slot) {
-                float2 v = LCT_LDG(f + 2 * P::template freq_of<1>(pos, slot));
+            // natural filter layout [kt][kh][kw]: even parity reads kw = 2f, odd parity kw = 2f + 1.  Half-rows layout
+            // (SYM, kFilterHalfRows): stored row min(kh, 2N - kh), times w_2N^kh when mirrored
+            const float2* f = SYM ? p.filt + ((size_t)kt * (N + 1) + sym_index<N>(kh)) * L
+                                  : p.filt + ((size_t)kt * L + kh) * L;
+            float2 rowtw = make_float2(1.f, 0.f);
+            if constexpr (SYM) rowtw = TwGlobal::get(sym_twist<N>(kh) * (kTwN / L));        // w_2N^kh for a mirrored row, else 1
+            auto filter_at = [&](int kw) {
+                float2 v = LCT_LDG(f + kw);
+                if constexpr (SYM) v = cmul(v, rowtw);
                 if (p.conj_filter) v.y = -v.y;
-                w[slot] = v;
-            });
+                return v;
+            };
+            float2 w[P::E], a[P::E];
+            for_each_slot<P, 1>(tau, [&](int pos, int slot) { w[slot] = filter_at(2 * P::template freq_of<1>(pos, slot)); });
             fwd_stage<P, 1, false, TwL>(tau,
                 [&](int pos, int) { return ze[padpos(pos)]; },
                 [&](int, int slot, float2 v) { a[slot] = cmul(v, w[slot]); });
             inv_stage<P, 1, false, TwL>(tau,
                 [&](int, int slot) { return a[slot]; },
                 [&](int pos, int, float2 v) { ze[padpos(pos)] = v; });
-            for_each_slot<P, 1>(tau, [&](int pos, int slot) {
-                float2 v = LCT_LDG(f + 2 * P::template freq_of<1>(pos, slot) + 1);
-                if (p.conj_filter) v.y = -v.y;
-                w[slot] = v;
-            });
+            for_each_slot<P, 1>(tau, [&](int pos, int slot) { w[slot] = filter_at(2 * P::template freq_of<1>(pos, slot) + 1); });
             fwd_stage<P, 1, false, TwL>(tau,
                 [&](int pos, int) { return zo[padpos(pos)]; },
                 [&](int, int slot, float2 v) { a[slot] = cmul(v, w[slot]); });
@@ -1298,6 +1387,10 @@ template <class K, int PH> struct PhaseLoop {
 template <class K> __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) lct_kernel(const Params p, const int iters) {
     extern __shared__ __align__(16) unsigned char smem[];
     typename K::Regs r;
+    if (p.stagger_ns > 0) {
+        const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x;
+        if (lin >= (unsigned)p.sms && lin < 2u * (unsigned)p.sms) __nanosleep((unsigned)p.stagger_ns);
+    }
     if constexpr (has_prologue<K>::value) {
         K::prologue(p, r, smem, threadIdx.x, blockIdx.x, blockIdx.y);
         __syncthreads();

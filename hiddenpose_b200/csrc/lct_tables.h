@@ -23,6 +23,11 @@ namespace lct {
 constexpr int kEllStride = 32;                        // == TimeTile::CT (static_assert in the kernels)
 
 struct EllRow { int32_t offset; float w[3]; };       // 16 bytes, loaded as float4
+// The time-forward kernel consumes rows in pairs (2p, 2p+1) -- the real and imaginary input of the packed-real
+// FFT -- and the two bands overlap: outside the first few pairs their union spans at most three columns.  Such a
+// pair is one 32-byte record: the union's offset, row 2p's three weights, row 2p+1's three weights (zero where a
+// row does not reach), so three tile loads feed six multiply-adds.
+struct PairRow { int32_t offset; float a[3]; float b[3]; float pad; };     // 32 bytes, loaded as two float4
 
 struct HostTables {
     int M = 0;
@@ -30,6 +35,7 @@ struct HostTables {
     std::vector<int32_t> mtx_rowptr;
     std::vector<float> mtx_vals_falloff, mtx_vals;
     std::vector<EllRow> mtx_ell_falloff, mtx_ell;
+    std::vector<PairRow> mtx_pair_falloff, mtx_pair;
     // mtxi rows (K5)
     std::vector<int32_t> mtxi_rowptr;
     std::vector<float> mtxi_vals, mtxi_vals_falloff;
@@ -41,15 +47,33 @@ inline std::vector<EllRow> make_ell(int M, const std::vector<int32_t>& rowptr, c
     std::vector<EllRow> ell(M);
     for (int i = 0; i < M; ++i) {
         const int len = rowptr[i + 1] - rowptr[i];
-        ell[i].offset = (len > 0 ? start[i] : 0) * kEllStride;
+        // the low bits of the offset (free: it is a multiple of kEllStride) carry the number of entries past the third
+        ell[i].offset = (len > 0 ? start[i] : 0) * kEllStride + (len > 3 ? len - 3 : 0);
         for (int e = 0; e < 3; ++e) ell[i].w[e] = (e < len) ? vals[rowptr[i] + e] : 0.0f;
     }
     return ell;
 }
 
+// Pair records for pairs >= long_pairs (earlier pairs are zero-filled: the kernel takes the row records for them).
+inline std::vector<PairRow> make_pairs(int M, const std::vector<int32_t>& rowptr, const std::vector<int32_t>& start,
+                                       const std::vector<float>& vals, int long_pairs) {
+    std::vector<PairRow> pr(M / 2);
+    std::memset(pr.data(), 0, sizeof(PairRow) * pr.size());
+    for (int p = long_pairs; p < M / 2; ++p) {
+        const int r0 = 2 * p, r1 = 2 * p + 1;
+        const int l0 = rowptr[r0 + 1] - rowptr[r0], l1 = rowptr[r1 + 1] - rowptr[r1];
+        const int u = l0 > 0 ? (l1 > 0 ? (start[r0] < start[r1] ? start[r0] : start[r1]) : start[r0]) : (l1 > 0 ? start[r1] : 0);
+        pr[p].offset = u * kEllStride;
+        for (int e = 0; e < l0; ++e) pr[p].a[start[r0] + e - u] = vals[rowptr[r0] + e];
+        for (int e = 0; e < l1; ++e) pr[p].b[start[r1] + e - u] = vals[rowptr[r1] + e];
+    }
+    return pr;
+}
+
 // Returns "" on success, otherwise a description of what is wrong with the operator.
 inline std::string build_tables(int M, const int32_t* rowptr, const int32_t* colidx, const float* vals,
-                                const float* falloff /* M or null */, int tail_rows, HostTables& t) {
+                                const float* falloff /* M or null */, int tail_rows, HostTables& t, int long_pairs = -1) {
+    if (long_pairs < 0) long_pairs = M / 2;               // no pair records wanted
     t.M = M;
     if (rowptr[0] != 0) return "CSR row pointers must start at 0";
     const int nnz = rowptr[M];
@@ -73,7 +97,17 @@ inline std::string build_tables(int M, const int32_t* rowptr, const int32_t* col
     for (int i = 0; i < M; ++i) {
         if (rowptr[i + 1] - rowptr[i] > 3 && i >= tail_rows)
             return "operator rows with more than 3 entries must be among the first " + std::to_string(tail_rows) + " rows";
+        if (rowptr[i + 1] - rowptr[i] - 3 >= kEllStride) return "operator rows must have fewer than " + std::to_string(kEllStride + 3) + " entries";
         if (t_count[i] > 3) return "operator columns must have at most 3 entries";
+    }
+    for (int p = long_pairs; p < M / 2; ++p) {
+        const int r0 = 2 * p, r1 = 2 * p + 1;
+        const int l0 = rowptr[r0 + 1] - rowptr[r0], l1 = rowptr[r1 + 1] - rowptr[r1];
+        if (l0 == 0 || l1 == 0) continue;
+        const int lo = start[r0] < start[r1] ? start[r0] : start[r1];
+        const int e0 = start[r0] + l0, e1 = start[r1] + l1;
+        if ((e0 > e1 ? e0 : e1) - lo > 3)
+            return "operator row pairs (2p, 2p+1) beyond the first " + std::to_string(long_pairs) + " must span at most 3 columns together";
     }
     t.mtx_rowptr.assign(rowptr, rowptr + M + 1);
     t.mtx_vals.assign(vals, vals + nnz);
@@ -81,6 +115,8 @@ inline std::string build_tables(int M, const int32_t* rowptr, const int32_t* col
     for (int e = 0; e < nnz; ++e) t.mtx_vals_falloff[e] = vals[e] * fall[colidx[e]];   // x*gridz^p (tflct.py:123-127)
     t.mtx_ell = make_ell(M, t.mtx_rowptr, start, t.mtx_vals);
     t.mtx_ell_falloff = make_ell(M, t.mtx_rowptr, start, t.mtx_vals_falloff);
+    t.mtx_pair = make_pairs(M, t.mtx_rowptr, start, t.mtx_vals, long_pairs);
+    t.mtx_pair_falloff = make_pairs(M, t.mtx_rowptr, start, t.mtx_vals_falloff, long_pairs);
 
     // transpose: mtxi = mtx^T (helper.py:61)
     t.mtxi_rowptr.assign(M + 1, 0);

@@ -55,6 +55,8 @@ extern "C" {
 
 /* lct_desc.flags */
 #define LCT_FLAG_NO_PLANE_FUSION 1   /* keep K2/K3/K4 as three kernels even when the plane fits on chip */
+#define LCT_FLAG_FULL_FILTER 2       /* store the whole half-spectrum filter even when its mirror symmetry in kh / kw
+                                        would allow the quarter layout (a quarter of the filter bytes per launch) */
 
 typedef struct lct_plan lct_plan;
 

@@ -46,13 +46,16 @@ class EmuPlan:
         self.falloff = np.ascontiguousarray(ops.falloff(M, material), np.float32)
         w = ops.inverse_filter_half(N, M, ops.slope_for(M, bin_len, wall_size), method)
         self.filt = np.ascontiguousarray((w * np.float32(1.0 / (8.0 * M * N * N))).astype(np.complex64))
+        # symmetric layouts (Params::filt_sym): frequencies kh, kw <= N only (quarter), or kh <= N only for the
+        # 512-point kernel (half rows)
+        self.filt_quarter = np.ascontiguousarray(self.filt[:, :N + 1, :N + 1] if N < 256 else self.filt[:, :N + 1, :])
         # fused layout [kt][kw/2][plane row][kw&1], rows in the H plan's position order (what lct_plan_create builds)
         L = 2 * N
         kh = np.array([lib().lct_emu_plane_row_freq(N, r) for r in range(L)])
         self.filt_plane = (np.ascontiguousarray(self.filt[:, kh, :].reshape(M + 1, L, N, 2).transpose(0, 2, 1, 3))
                            if N <= 64 else None)
 
-    def run(self, inp, D, Tin, be, backward=False, mask=31, reverse=False, s1=None, s2=None, fused=True, drift=0):
+    def run(self, inp, D, Tin, be, backward=False, mask=31, reverse=False, s1=None, s2=None, fused=True, drift=0, sym=False):
         M, N = self.M, self.N
         inp = np.ascontiguousarray(inp, dtype=np.float32)
         C = inp.shape[0]
@@ -72,9 +75,9 @@ class EmuPlan:
             M, N, C, D, Tin, int(be[0]), None if uniform else _p(be, i32),
             _p(inp, f), _p(out, f), _p(s1.view(np.float32), f), _p(s2.view(np.float32), f),
             _p(self.csr[0], i32), _p(self.csr[1], i32), _p(self.csr[2], f), _p(self.falloff, f),
-            _p(self.filt.view(np.float32), f),
+            _p((self.filt_quarter if sym else self.filt).view(np.float32), f),
             _p(self.filt_plane.view(np.float32), f) if (fused and self.filt_plane is not None) else None,
-            int(backward), int(mask))
+            int(backward), int(mask), (2 if self.N >= 256 else 1) if sym else 0)
         lib().lct_emu_set_drift(0)
         assert rc == 0, rc
         return out, s1, s2

@@ -118,20 +118,24 @@ void lct_emu_init(int reverse_threads) {
 
 void lct_emu_set_drift(int mode) { g_drift = mode; }
 
-// All pointers are host pointers.  `filt` must already carry the 1/(8 M N N) scale.  The operator
+// All pointers are host pointers.  `filt` must already carry the 1/(8 M N N) scale; with filt_sym != 0 it is the
+// quarter layout (M+1, N+1, N+1) of Params::filt_sym.  The operator
 // arrives as the CSR of mtx plus the falloff vector, exactly as lct_plan_create receives it.
 int lct_emu_run(int M, int N, int C, int D, int Tin, int be_uniform, const int* be,
                 const float* in, float* out, float* s1, float* s2,
                 const int* mtx_rowptr, const int* mtx_colidx, const float* mtx_vals, const float* falloff,
-                const float* filt, const float* filt_plane, int backward, int mask) {
+                const float* filt, const float* filt_plane, int backward, int mask, int filt_sym) {
     lct::HostTables ht;
-    if (!lct::build_tables(M, mtx_rowptr, mtx_colidx, mtx_vals, falloff, lct::time_tail_rows(M), ht).empty()) return 100;
-    auto band = [](const std::vector<lct::EllRow>& e, const std::vector<int32_t>& rp, const std::vector<float>& v) {
-        return lct::BandTable{reinterpret_cast<const float4*>(e.data()), rp.data(), v.data()};
+    if (!lct::build_tables(M, mtx_rowptr, mtx_colidx, mtx_vals, falloff, lct::time_tail_rows(M), ht, lct::time_long_pairs(M)).empty()) return 100;
+    auto band = [](const std::vector<lct::EllRow>& e, const std::vector<int32_t>& rp, const std::vector<float>& v,
+                   const std::vector<lct::PairRow>* pr = nullptr) {
+        return lct::BandTable{reinterpret_cast<const float4*>(e.data()), rp.data(), v.data(),
+                              pr ? reinterpret_cast<const float4*>(pr->data()) : nullptr};
     };
-    lct::ChainTables t{band(ht.mtx_ell_falloff, ht.mtx_rowptr, ht.mtx_vals_falloff), band(ht.mtx_ell, ht.mtx_rowptr, ht.mtx_vals),
+    lct::ChainTables t{band(ht.mtx_ell_falloff, ht.mtx_rowptr, ht.mtx_vals_falloff, &ht.mtx_pair_falloff),
+                       band(ht.mtx_ell, ht.mtx_rowptr, ht.mtx_vals, &ht.mtx_pair),
                        band(ht.mtxi_ell, ht.mtxi_rowptr, ht.mtxi_vals), band(ht.mtxi_ell_falloff, ht.mtxi_rowptr, ht.mtxi_vals_falloff),
-                       reinterpret_cast<const float2*>(filt), reinterpret_cast<const float2*>(filt_plane)};
+                       reinterpret_cast<const float2*>(filt), reinterpret_cast<const float2*>(filt_plane), filt_sym};
     EmuLauncher l;
     return lct::run_chain(l, t, M, N, C, D, Tin, be_uniform, be, 0, in, out,
                           reinterpret_cast<float2*>(s1), reinterpret_cast<float2*>(s2), backward != 0, mask);

@@ -130,6 +130,33 @@ def test_emulated_kernels_match_reference(name):
     assert c.gx_err(gx.reshape(c.B, c.D, c.tin, c.N, c.N)) <= 1e-4
 
 
+@pytest.mark.parametrize("name,N,M", [("m32n256_window", 256, 32), (None, 16, 32), (None, 64, 32)])
+def test_emulated_quarter_filter_matches_full(name, N, M):
+    """The filter's mirror symmetry in kh and kw (Params::filt_sym): the column-filter kernels reading the stored
+    quarter times a twiddle give what they give reading the whole half spectrum -- forward and backward, the
+    parity-split kernel (N = 256) and the register-cached one -- and the reference's own output where a golden exists."""
+    from tests.emu.emu import EmuPlan
+    if name:
+        c = Case(name)
+        plan = EmuPlan(c.N, c.M, c.bin_len)
+        x, g, tin, tbes = c.x.reshape(c.B * c.D, c.tin, N, N), c.g.reshape(c.B * c.D, M, N, N), c.tin, c.tbes
+    else:
+        plan = EmuPlan(N, M, 0.16)
+        rs = np.random.RandomState(N)
+        tin, tbes = M - 4, [3]
+        x, g = rs.rand(1, tin, N, N).astype(np.float32), rs.randn(1, M, N, N).astype(np.float32)
+    full = plan.run(x, 1, tin, tbes, fused=False)[0]
+    quarter = plan.run(x, 1, tin, tbes, fused=False, sym=True)[0]
+    assert O.rel_l2(quarter, full) <= 1e-6
+    gfull = plan.run(g, 1, tin, tbes, backward=True, fused=False)[0]
+    gquarter = plan.run(g, 1, tin, tbes, backward=True, fused=False, sym=True)[0]
+    assert O.rel_l2(gquarter, gfull) <= 1e-6
+    assert np.array_equal(quarter, plan.run(x, 1, tin, tbes, fused=False, sym=True, reverse=True)[0])
+    if name:
+        assert c.y_err(quarter.reshape(c.B, c.D, M, N, N)) <= 1e-5
+        assert c.gx_err(gquarter.reshape(c.B, c.D, tin, N, N)) <= 1e-4
+
+
 def test_emulated_kernels_have_no_intra_phase_races():
     """Running the threads of each barrier-delimited phase in reverse order must not change a bit."""
     from tests.emu.emu import EmuPlan
