@@ -60,3 +60,58 @@ def reference_layer(spatial, crop, bin_len, wall_size=2.0, method="lct", materia
     assert layer.crop == crop
     layer.todev("cpu", dnum)
     return layer
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Downstream of the layer (tests/test_downstream.py only): the reference's own FeatureExtraction, normalize_feature,
+# UNet3d, posenet3d_50 and soft-argmax, imported unmodified from baseline/_ref.
+# ------------------------------------------------------------------------------------------------------------------
+DOWNSTREAM_FILES = ("models/feature_extraction.py", "models/feature_propagation.py", "models/posenet3d_50.py",
+                    "unet/unet3d.py", "utils/criterion.py")
+
+
+def downstream_available():
+    return available() and all(os.path.isfile(os.path.join(REF_DIR, f)) for f in DOWNSTREAM_FILES)
+
+
+def _stub_unreachable_imports():
+    """unet/unet3d.py imports its training-script dependencies at module level (torchsummary, the data loader, the yacs
+    config); none is used by the network itself.  They are satisfied with empty stand-ins."""
+    import types
+
+    class CfgNode(dict):
+        __getattr__ = dict.get
+
+        def __setattr__(self, k, v):
+            self[k] = v
+
+    def module(name, **attrs):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[name] = m
+        return sys.modules[name]
+
+    module("torchsummary", summary=lambda *a, **k: None)
+    module("yacs")
+    module("yacs.config", CfgNode=CfgNode)
+    module("config")
+    module("config.config_noise", _C=CfgNode())
+    module("utils.nlos_dataloader", NlosDataset=object)
+
+
+def downstream_modules():
+    """(FeatureExtraction, normalize_feature, UNet3d, get_pose_net_50, softmax_integral_tensor) of the reference."""
+    if not downstream_available():
+        raise RuntimeError("the reference's downstream modules are not staged under baseline/_ref")
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import utils.helper  # noqa: F401  (makes `utils` the staged package before the stand-in submodule is attached)
+    _stub_unreachable_imports()
+    from models.feature_extraction import FeatureExtraction
+    from models.feature_propagation import normalize_feature
+    from models.posenet3d_50 import get_pose_net_50
+    from unet.unet3d import UNet3d
+    from utils.criterion import softmax_integral_tensor
+    return FeatureExtraction, normalize_feature, UNet3d, get_pose_net_50, softmax_integral_tensor

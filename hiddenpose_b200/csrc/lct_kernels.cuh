@@ -1108,7 +1108,30 @@ template <class P, int RB_, bool SYM = false> struct ColFilterSplit {
     static constexpr int RS = N + P::R0 * PAD + ((P::TL < 16) ? 8 : 0);    // row stride in float2
     static constexpr size_t kSmem = TwL::kBytes + (size_t)2 * RB * RS * sizeof(float2);     // even and odd exchange rows
     static constexpr int kFiltPitch = L;                                   // stored filter row, in values (kFilterHalfRows keeps whole rows)
-    struct Regs { float2 in[P::E]; };
+    // Requesting the even parity's filter values a stage early (before the odd stage-0 transform) and the odd parity's
+    // before the even inverse stage was measured at cfg5: 527 vs 496 us -- the 32 values held across the stage push the
+    // kernel from 60 to 116 bytes of spills at its 128-register cap, which costs more than the hidden latency returns.
+#ifndef LCT_K3S_EARLY_FILTER
+#define LCT_K3S_EARLY_FILTER 0
+#endif
+    static constexpr bool kEarlyFilter = LCT_K3S_EARLY_FILTER != 0;
+    struct Regs { float2 in[P::E]; float2 w[P::E]; };
+
+    // r.w <- the filter values of this thread's stage-1 slots for one output parity (kw = 2 f + parity).
+    // Natural layout [kt][kh][kw]; half-rows layout (SYM, kFilterHalfRows): stored row min(kh, 2N - kh), times w_2N^kh
+    // when mirrored (one row-constant twiddle).
+    static LCT_DEV void load_filter(const Params& p, Regs& r, int tau, int kt, int kh, int parity) {
+        const float2* f = SYM ? p.filt + ((size_t)kt * (N + 1) + sym_index<N>(kh)) * L
+                              : p.filt + ((size_t)kt * L + kh) * L;
+        float2 rowtw = make_float2(1.f, 0.f);
+        if constexpr (SYM) rowtw = TwGlobal::get(sym_twist<N>(kh) * (kTwN / L));
+        for_each_slot<P, 1>(tau, [&](int pos, int slot) {
+            float2 v = LCT_LDG(f + 2 * P::template freq_of<1>(pos, slot) + parity);
+            if constexpr (SYM) v = cmul(v, rowtw);
+            if (p.conj_filter) v.y = -v.y;
+            r.w[slot] = v;
+        });
+    }
     static void grid(const Params& p, int& gx, int& gy) { gx = L / RB; gy = p.M + 1; }
     static int iterations(const Params& p) { return p.C; }
     static LCT_DEV int padpos(int pos) { return pos + (pos / P::st(0)) * PAD; }
@@ -1154,35 +1177,27 @@ template <class P, int RB_, bool SYM = false> struct ColFilterSplit {
             fwd_stage<P, 0, false, TwL>(tau,
                 [&](int, int slot) { return r.in[slot]; },
                 [&](int pos, int, float2 v) { ze[padpos(pos)] = v; });
+            // the even parity's filter values are requested here, a whole stage before their first use: at one channel
+            // per launch nothing else hides their latency (it was 22 % of the kernel's stall samples)
+            if constexpr (kEarlyFilter) load_filter(p, r, tau, kt, kh, 0);
             fwd_stage<P, 0, false, TwL>(tau,
                 [&](int pos, int slot) { return TwGlobal::mul(r.in[slot], pos * (kTwN / L)); },
                 [&](int pos, int, float2 v) { zo[padpos(pos)] = v; });
             if (it + 1 < p.C) fetch(row + chan, tau, r);        // next channel's row flies during this one's math
         } else if constexpr (PH == 1) {
-            // natural filter layout [kt][kh][kw]: even parity reads kw = 2f, odd parity kw = 2f + 1.  Half-rows layout
-            // (SYM, kFilterHalfRows): stored row min(kh, 2N - kh), times w_2N^kh when mirrored
-            const float2* f = SYM ? p.filt + ((size_t)kt * (N + 1) + sym_index<N>(kh)) * L
-                                  : p.filt + ((size_t)kt * L + kh) * L;
-            float2 rowtw = make_float2(1.f, 0.f);
-            if constexpr (SYM) rowtw = TwGlobal::get(sym_twist<N>(kh) * (kTwN / L));        // w_2N^kh for a mirrored row, else 1
-            auto filter_at = [&](int kw) {
-                float2 v = LCT_LDG(f + kw);
-                if constexpr (SYM) v = cmul(v, rowtw);
-                if (p.conj_filter) v.y = -v.y;
-                return v;
-            };
-            float2 w[P::E], a[P::E];
-            for_each_slot<P, 1>(tau, [&](int pos, int slot) { w[slot] = filter_at(2 * P::template freq_of<1>(pos, slot)); });
+            float2 a[P::E];
+            if constexpr (!kEarlyFilter) load_filter(p, r, tau, kt, kh, 0);
             fwd_stage<P, 1, false, TwL>(tau,
                 [&](int pos, int) { return ze[padpos(pos)]; },
-                [&](int, int slot, float2 v) { a[slot] = cmul(v, w[slot]); });
+                [&](int, int slot, float2 v) { a[slot] = cmul(v, r.w[slot]); });
+            if constexpr (kEarlyFilter) load_filter(p, r, tau, kt, kh, 1);          // odd parity: flies during the even inverse stage
             inv_stage<P, 1, false, TwL>(tau,
                 [&](int, int slot) { return a[slot]; },
                 [&](int pos, int, float2 v) { ze[padpos(pos)] = v; });
-            for_each_slot<P, 1>(tau, [&](int pos, int slot) { w[slot] = filter_at(2 * P::template freq_of<1>(pos, slot) + 1); });
+            if constexpr (!kEarlyFilter) load_filter(p, r, tau, kt, kh, 1);
             fwd_stage<P, 1, false, TwL>(tau,
                 [&](int pos, int) { return zo[padpos(pos)]; },
-                [&](int, int slot, float2 v) { a[slot] = cmul(v, w[slot]); });
+                [&](int, int slot, float2 v) { a[slot] = cmul(v, r.w[slot]); });
             inv_stage<P, 1, false, TwL>(tau,
                 [&](int, int slot) { return a[slot]; },
                 [&](int pos, int, float2 v) { zo[padpos(pos)] = v; });
