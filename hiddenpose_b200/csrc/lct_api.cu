@@ -341,7 +341,7 @@ int lct_plan_create(const lct_desc* d, lct_plan** out) {
 
     // validate the operator and derive the banded row tables for mtx and mtxi = mtx^T (helper.py:61)
     lct::HostTables ht;
-    const std::string why = lct::build_tables(M, d->mtx_rowptr, d->mtx_colidx, d->mtx_vals, d->falloff, lct::time_tail_rows(M), ht, lct::time_long_pairs(M));
+    const std::string why = lct::build_tables(M, d->mtx_rowptr, d->mtx_colidx, d->mtx_vals, d->falloff, lct::time_tail_rows(M), ht, lct::time_long_pairs(M), lct::time_tile_columns(M));
     if (!why.empty()) return fail(LCT_ERR_INVALID, why.c_str());
 
     lct_plan* p = new (std::nothrow) lct_plan();
@@ -581,12 +581,12 @@ int lct_minmax(const float* x, int32_t channels, int64_t elems, void* keys, void
     return LCT_OK;
 }
 
-int lct_normalize_feature(const float* x, const void* keys, float* out, int32_t channels, int64_t elems,
+int lct_normalize_feature(const float* x, void* keys, float* out, int32_t channels, int64_t elems,
                           float scale, void* stream_) {
     if (!x || !keys || !out || channels <= 0 || elems <= 0 || (((uintptr_t)x | (uintptr_t)out) & 15))
         return fail(LCT_ERR_INVALID, "bad argument");
     lct::normalize_kernel<<<dim3(reduce_blocks(elems, channels), channels), 256, 0, (cudaStream_t)stream_>>>(
-        x, out, static_cast<const unsigned long long*>(keys), elems, scale);
+        x, out, static_cast<unsigned long long*>(keys), elems, scale);
     LCT_CUDA(cudaGetLastError());
     return LCT_OK;
 }

@@ -38,7 +38,11 @@ template <> struct LinePlan<256> { using type = Plan<16, 16>; };
 template <> struct LinePlan<512> { using type = Plan<32, 16>; };        // (16,32) measured the same
 
 // column tile (in columns of the flattened H*W axis) for the T-axis kernels
-template <int M> struct TimeTile { static constexpr int CT = 32; };     // 16-wide tiles measured slower at every M
+#ifndef LCT_TIME_TILE_512
+#define LCT_TIME_TILE_512 32
+#endif
+template <int M> struct TimeTile { static constexpr int CT = (M >= 512) ? LCT_TIME_TILE_512 : 32; };
+inline int time_tile_columns(int M) { return M >= 512 ? LCT_TIME_TILE_512 : 32; }
 // column tile along W for the H-axis kernels
 template <int N> struct RowTile { static constexpr int CT = (N >= 256) ? 16 : (N < 32 ? N : 32); };
 // rows per block for K3

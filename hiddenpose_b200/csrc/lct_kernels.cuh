@@ -28,6 +28,7 @@
 // (SURVEY.md section 3.5).
 #pragma once
 
+#include <limits>
 #include <type_traits>
 
 #include "lct_fft.cuh"
@@ -254,6 +255,11 @@ struct TileWalk {
     LCT_HD int iterations() const { return (total + G - 1) / G; }
 };
 
+#ifdef LCT_EMULATE
+static const float kInfinity = std::numeric_limits<float>::infinity();
+#else
+#define kInfinity __int_as_float(0x7f800000)
+#endif
 // order-preserving key of a float and its position (see lct_normalize.cuh)
 LCT_DEV unsigned long long minmax_key(float v, unsigned int pos, bool is_max) {
     const unsigned int b = (unsigned int)float_bits(v);
@@ -261,8 +267,17 @@ LCT_DEV unsigned long long minmax_key(float v, unsigned int pos, bool is_max) {
     if (v != v) k = is_max ? 0xffffffffu : 0u;         // NaN wins both reductions (torch.min / torch.max propagate it)
     return is_max ? ~(((unsigned long long)k << 32) | (0xffffffffu - pos)) : (((unsigned long long)k << 32) | pos);
 }
-LCT_DEV void minmax_commit(unsigned long long* keys, int c, unsigned long long kmin, unsigned long long kmax) {
+// Block-level commit of the per-thread keys: warp shuffle reduction, then one shared-memory atomicMin pair per warp
+// into the block's slot; the warp that arrives last (a shared counter tells) carries the slot to the channel's global
+// keys and re-arms it.  One global atomic pair per block and tile instead of one per warp: at 16 x 128^3 the 16 warps
+// x 512 tiles hammering one address per channel cost 36 us per step.  `slot` = {min key, max key, arrivals}, 24 bytes
+// of shared memory initialised to {~0, ~0, 0}; every warp of the block must call (warp-uniformly).
+struct MinMaxSlot { unsigned long long kmin, kmax; unsigned int arrived, pad; };
+LCT_DEV void minmax_slot_init(MinMaxSlot* slot) { slot->kmin = ~0ull; slot->kmax = ~0ull; slot->arrived = 0u; }
+LCT_DEV void minmax_commit(unsigned long long* keys, int c, unsigned long long kmin, unsigned long long kmax,
+                           MinMaxSlot* slot, int nwarps) {
 #ifdef LCT_EMULATE
+    (void)slot; (void)nwarps;
     if (kmin < keys[2 * c]) keys[2 * c] = kmin;
     if (kmax < keys[2 * c + 1]) keys[2 * c + 1] = kmax;
 #else
@@ -273,30 +288,38 @@ LCT_DEV void minmax_commit(unsigned long long* keys, int c, unsigned long long k
         kmax = b < kmax ? b : kmax;
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicMin(keys + 2 * c, kmin);
-        atomicMin(keys + 2 * c + 1, kmax);
+        atomicMin(&slot->kmin, kmin);
+        atomicMin(&slot->kmax, kmax);
+        __threadfence_block();
+        if (atomicAdd(&slot->arrived, 1u) == (unsigned int)nwarps - 1u) {      // last warp of the block for this tile
+            __threadfence_block();
+            atomicMin(keys + 2 * c, atomicExch(&slot->kmin, ~0ull));
+            atomicMin(keys + 2 * c + 1, atomicExch(&slot->kmax, ~0ull));
+            slot->arrived = 0u;               // nobody touches the slot again before the next tile's barriers
+        }
     }
 #endif
 }
-
 
 // sum_e w[e] * src[(start + e) * kEllStride] for one operator row; `src` must have two readable
 // (finite) rows past the last one, because short rows still touch three.  The record carries
 // start * kEllStride; rows longer than three continue in the CSR arrays, and the host guarantees
 // (build_tables) that such rows exist only where the caller passes kTail = true.
-template <bool kTail>
+template <bool kTail, int STRIDE = kEllStride>
 LCT_DEV float band_dot(const Params& p, const float4* ell, int row, const float* src) {
     const float4 e = ell[row];                     // block-local copy in shared memory (warp-uniform: broadcast)
     // the low bits of the offset hold the number of entries past the third; they are zero wherever kTail is false
-    const int off = float_bits(e.x), extra = kTail ? (off & (kEllStride - 1)) : 0;
+    const int off = float_bits(e.x), extra = kTail ? (off & (STRIDE - 1)) : 0;
     const float* s = src + (off - extra);
     float acc = e.y * s[0];
-    acc = fmaf(e.z, s[kEllStride], acc);
-    acc = fmaf(e.w, s[2 * kEllStride], acc);
+    acc = fmaf(e.z, s[STRIDE], acc);
+    acc = fmaf(e.w, s[2 * STRIDE], acc);
     if constexpr (kTail) {
         if (extra) {                               // rare (the first ~sqrt(M)/6 rows of mtx): the CSR arrays hold the rest
-            const float* v = p.vals + LCT_LDG(p.rowptr + row);
-            for (int k = 3; k < 3 + extra; ++k) acc = fmaf(LCT_LDG(v + k), s[k * kEllStride], acc);
+            const int first = LCT_LDG(p.rowptr + row);
+            const int len = extra < STRIDE - 1 ? 3 + extra : LCT_LDG(p.rowptr + row + 1) - first;      // the count saturates
+            const float* v = p.vals + first;
+            for (int k = 3; k < len; ++k) acc = fmaf(LCT_LDG(v + k), s[k * STRIDE], acc);
         }
     }
     return acc;
@@ -304,10 +327,11 @@ LCT_DEV float band_dot(const Params& p, const float4* ell, int row, const float*
 
 // Rows (2 pair, 2 pair + 1) of the operator applied together through one pair record (lct_tables.h): three tile
 // loads, six multiply-adds.  Only valid for pairs >= kLongPairs (build_tables checks the operator).
+template <int STRIDE = kEllStride>
 LCT_DEV float2 pair_dot(const float4* pairs, int pair, const float* src) {
     const float4 a = pairs[2 * pair], b = pairs[2 * pair + 1];       // {offset, a0, a1, a2}, {b0, b1, b2, -}
     const float* s = src + float_bits(a.x);
-    const float x0 = s[0], x1 = s[kEllStride], x2 = s[2 * kEllStride];
+    const float x0 = s[0], x1 = s[STRIDE], x2 = s[2 * STRIDE];
     return make_float2(fmaf(a.w, x2, fmaf(a.z, x1, a.y * x0)), fmaf(b.z, x2, fmaf(b.y, x1, b.x * x0)));
 }
 
@@ -318,6 +342,9 @@ LCT_DEV int window_begin(const Params& p, int c) {
 // Stage-0 butterfly inputs q < Q of the time-forward kernel cover the pairs whose two rows may span more than three
 // columns together (pairs up to ~M/10 of helper.py:35-69's operator: 1 / 4 / 10 / 24 / 53 at M = 32 ... 512); the
 // rest take one pair record each.  build_tables refuses an operator that does not fit.
+// (Measured: the pair records take K1 from 246 to 226 us at 8 x 512x128x128 and from 94 to 90 us at 16 x 128^3; at
+//  M = 256, where the kernel's time is fixed ramp-up and tail rather than instruction issue, they change nothing.
+//  Keeping each thread's pair offsets in registers across the tile walk of the persistent kernel: no gain either.)
 template <int M> struct TimeLongQ { static constexpr int Q = (M >= 512) ? 4 : ((M >= 128) ? 2 : 1); };
 
 // ---------------------------------------------------------------------------
@@ -328,7 +355,6 @@ template <int M> struct TimeLongQ { static constexpr int Q = (M >= 512) ? 4 : ((
 template <class P, int CT_> struct TimeFwd {
     using TwS = TwNone;                        // constant-bank twiddles (a block-local table measured slower here)
     static constexpr int M = P::L, CT = CT_, kThreads = P::TL * CT;
-    static_assert(CT == kEllStride, "the operator records carry offsets for kEllStride-column tiles");
     // phases: load x tile | gather + stage 0 -> zs | stages 1.. in place | post-process
     static constexpr int kPhases = 2 + (P::S - 1) + 1;
     // x tile, FFT buffer and the operator's row records side by side: the register file already caps
@@ -400,10 +426,10 @@ template <class P, int CT_> struct TimeFwd {
                     // by row -- and rows longer than three taps sit below 2 * st(0): the first input of a butterfly only
                     const float4* pairs = reinterpret_cast<const float4*>(smem + kWork);
                     const float4* ell = pairs + M;
-                    if (slot % P::radix(0) >= kLongQ) return pair_dot(pairs, pos, xs + col);
+                    if (slot % P::radix(0) >= kLongQ) return pair_dot<CT>(pairs, pos, xs + col);
                     if (slot % P::radix(0) == 0)
-                        return make_float2(band_dot<true>(p, ell, 2 * pos, xs + col), band_dot<true>(p, ell, 2 * pos + 1, xs + col));
-                    return make_float2(band_dot<false>(p, ell, 2 * pos, xs + col), band_dot<false>(p, ell, 2 * pos + 1, xs + col));
+                        return make_float2(band_dot<true, CT>(p, ell, 2 * pos, xs + col), band_dot<true, CT>(p, ell, 2 * pos + 1, xs + col));
+                    return make_float2(band_dot<false, CT>(p, ell, 2 * pos, xs + col), band_dot<false, CT>(p, ell, 2 * pos + 1, xs + col));
                 },
                 [&](int pos, int, float2 v) { zs[pos * CT + col] = v; });
         } else if constexpr (PH < 1 + P::S) {
@@ -453,7 +479,6 @@ template <class P, int CT_> struct TimeFwd {
 template <class P, int CT_> struct TimeFwdPersistent {
     using TwS = TwNone;                        // constant-bank twiddles (a block-local table measured slower here)
     static constexpr int M = P::L, CT = CT_, kThreads = P::TL * CT;
-    static_assert(CT == kEllStride, "the operator records carry offsets for kEllStride-column tiles");
     // phases: load x tile | gather + stage 0 -> zs | stages 1.. in place | post-process
     static constexpr int kPhases = 2 + (P::S - 1) + 1;
     // x tile, FFT buffer and the operator's row records side by side: the register file already caps
@@ -521,7 +546,7 @@ template <class P, int CT_> struct TimeFwdPersistent {
         if constexpr (PH == 0 && kPersist) {
             if (it == 0) {
                 for (int j = tid; j < M + kLongRows; j += kThreads)
-                reinterpret_cast<float4*>(smem + kWork)[j] = j < M ? LCT_LDG(p.pair + j) : LCT_LDG(p.ell + (j - M));
+                    reinterpret_cast<float4*>(smem + kWork)[j] = j < M ? LCT_LDG(p.pair + j) : LCT_LDG(p.ell + (j - M));
                 issue_tile(p, smem, tid, tile);
             }
             cp_async_wait_all();                             // later tiles were issued during the previous tile's stages
@@ -562,10 +587,10 @@ template <class P, int CT_> struct TimeFwdPersistent {
                     // by row -- and rows longer than three taps sit below 2 * st(0): the first input of a butterfly only
                     const float4* pairs = reinterpret_cast<const float4*>(smem + kWork);
                     const float4* ell = pairs + M;
-                    if (slot % P::radix(0) >= kLongQ) return pair_dot(pairs, pos, xs + col);
+                    if (slot % P::radix(0) >= kLongQ) return pair_dot<CT>(pairs, pos, xs + col);
                     if (slot % P::radix(0) == 0)
-                        return make_float2(band_dot<true>(p, ell, 2 * pos, xs + col), band_dot<true>(p, ell, 2 * pos + 1, xs + col));
-                    return make_float2(band_dot<false>(p, ell, 2 * pos, xs + col), band_dot<false>(p, ell, 2 * pos + 1, xs + col));
+                        return make_float2(band_dot<true, CT>(p, ell, 2 * pos, xs + col), band_dot<true, CT>(p, ell, 2 * pos + 1, xs + col));
+                    return make_float2(band_dot<false, CT>(p, ell, 2 * pos, xs + col), band_dot<false, CT>(p, ell, 2 * pos + 1, xs + col));
                 },
                 [&](int pos, int, float2 v) { zs[pos * CT + col] = v; });
         } else if constexpr (PH < 1 + P::S) {
@@ -617,13 +642,12 @@ template <class P, int CT_> struct TimeFwdPersistent {
 template <class P, int CT_> struct TimeInv {
     using TwS = TwNone;                        // constant-bank twiddles (a block-local table measured slower here)
     static constexpr int M = P::L, CT = CT_, kThreads = P::TL * CT;
-    static_assert(CT == kEllStride, "the operator records carry offsets for kEllStride-column tiles");
     static constexpr int kPhases = 2 + P::S + 1;          // load | stage S-1 -> regs | scatter | middle.. | stage 0 -> vol | gather
     // spectrum tile / FFT buffer (aliased: the first stage goes through registers) + the real volume
     // tile next to it (registers cap the kernel at two blocks per SM anyway; saves a phase)
     static constexpr size_t kZs = ((size_t)(M + 1) * CT * sizeof(float2) + 15) / 16 * 16;
     static constexpr size_t kWork = kZs + (size_t)(M + 2) * CT * sizeof(float);
-    static constexpr size_t kSmem = TwS::kBytes + (kWork + (size_t)M * sizeof(float4));       // + the operator's row records
+    static constexpr size_t kSmem = TwS::kBytes + (kWork + (size_t)M * sizeof(float4)) + 32;  // + the operator's row records + MinMaxSlot
     static constexpr bool kWarpSync = false;
     // 1024 threads/SM at <= 64 regs; the 32-wide butterflies need 128 regs (512 threads/SM)
     static constexpr int kMinBlocks = (P::E >= 32) ? (512 / kThreads > 0 ? 512 / kThreads : 1) : ((kThreads >= 1024) ? 1 : 1024 / kThreads);
@@ -632,7 +656,10 @@ template <class P, int CT_> struct TimeInv {
     static int iterations(const Params& p) { return TileWalk(p, p.N * p.N / CT).iterations(); }
 
     static constexpr bool kHasPrologue = true;
-    static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwS::fill(smem, tid, kThreads); }
+    static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) {
+        TwS::fill(smem, tid, kThreads);
+        if (tid == 0) minmax_slot_init(reinterpret_cast<MinMaxSlot*>(smem + TwS::kBytes + kWork + (size_t)M * sizeof(float4)));
+    }
 
     // spectrum tile -> zs[(M+1)][CT] c64 by 16-byte asynchronous copies (two columns each)
     static LCT_DEV void issue_tile(const Params& p, unsigned char* smem, int tid, int tile) {
@@ -714,37 +741,43 @@ template <class P, int CT_> struct TimeInv {
 #pragma unroll 8                                   // full unrolling (16) measured 2 % slower at M = 256
 #endif
                 for (int m = 0; m < M / P::TL; ++m, d += step)
-                    if (tau + m * P::TL < p.out_T) *d = band_dot<false>(p, er, m * P::TL, vc);
+                    if (tau + m * P::TL < p.out_T) *d = band_dot<false, CT>(p, er, m * P::TL, vc);
             } else {
-                // Ordered compares never select a NaN and the +-3.4e38 starting values hide an infinity, so the loop
-                // also folds every value into `poison` (v * 0 is 0 for finite v and NaN otherwise: one FFMA per
-                // value); a poisoned strip redoes its reduction on the integer keys, where NaN and +-inf are ordered.
-                float mn = 3.4e38f, mx = -3.4e38f, poison = 0.f;
-                int jmn = tau, jmx = tau;
+                // Values only (two FMNMX per output): the positions the backward of normalize_feature needs are found by
+                // the normalisation pass itself, which reads every value anyway (lct_normalize.cuh) -- the keys leave
+                // here with the position field at "unknown", which any real position beats.  Tracking the positions in
+                // this loop (two compares, two value selects, two index selects per output) cost 19 % of the kernel.
+                // FMNMX drops a NaN, so every value is also folded into `poison` (v * 0 is 0 for finite v, NaN for a NaN
+                // or an infinity: one FFMA per output); a poisoned strip redoes its reduction on the integer keys, where
+                // NaN wins both sides as it does in torch.min / torch.max.
+                float mn = kInfinity, mx = -kInfinity, poison = 0.f;
+                const float4* er = ell + be + tau;         // same loop shape as the plain path above
 #ifndef LCT_EMULATE
-#pragma unroll 4
+#pragma unroll 8
 #endif
-                for (int j = tau; j < p.out_T; j += P::TL, d += step) {
-                    const float v = band_dot<false>(p, ell, be + j, vc);
-                    *d = v;
-                    poison = fmaf(v, 0.f, poison);
-                    if (v < mn) { mn = v; jmn = j; }
-                    if (v > mx) { mx = v; jmx = j; }
-                }
+                for (int m = 0; m < M / P::TL; ++m, d += step)
+                    if (tau + m * P::TL < p.out_T) {
+                        const float v = band_dot<false, CT>(p, er, m * P::TL, vc);
+                        *d = v;
+                        poison = fmaf(v, 0.f, poison);
+                        mn = fminf(mn, v);
+                        mx = fmaxf(mx, v);
+                    }
                 const unsigned int base = (unsigned int)(col0 + col);
-                unsigned long long kmin = minmax_key(mn, (unsigned int)jmn * NN + base, false);
-                unsigned long long kmax = minmax_key(mx, (unsigned int)jmx * NN + base, true);
+                unsigned long long kmin = minmax_key(mn, 0xffffffffu, false);
+                unsigned long long kmax = minmax_key(mx, 0xffffffffu, true);
                 if (poison != 0.f) {                       // NaN or infinity somewhere in this thread's strip
                     kmin = ~0ull; kmax = ~0ull;
                     for (int j = tau; j < p.out_T; j += P::TL) {
-                        const float v = band_dot<false>(p, ell, be + j, vc);
+                        const float v = band_dot<false, CT>(p, ell, be + j, vc);
                         const unsigned long long a = minmax_key(v, (unsigned int)j * NN + base, false);
                         const unsigned long long b = minmax_key(v, (unsigned int)j * NN + base, true);
                         kmin = a < kmin ? a : kmin;
                         kmax = b < kmax ? b : kmax;
                     }
                 }
-                if (tau < p.out_T) minmax_commit(p.minmax_keys, p.c_base + c, kmin, kmax);
+                minmax_commit(p.minmax_keys, p.c_base + c, kmin, kmax,
+                              reinterpret_cast<MinMaxSlot*>(smem + kWork + (size_t)M * sizeof(float4)), kThreads / 32);
             }
         }
     }

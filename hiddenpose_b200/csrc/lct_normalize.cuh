@@ -84,20 +84,37 @@ __global__ void minmax_kernel(const float* __restrict__ x, unsigned long long* _
     }
 }
 
-// out = (x - mn) / ((mx - mn) + 1e-15) * scale, in the reference's operation order (bit-compatible with torch)
+// out = (x - mn) / ((mx - mn) + 1e-15) * scale, in the reference's operation order (bit-compatible with torch).
+// The keys may arrive from the LCT's last kernel with their position fields at "unknown" (it reduces values only);
+// this pass sees every value, so it writes the positions of the extremes back into the keys (lowest position wins,
+// as in the stand-alone reduction) for the backward pass to use.  The value half of a key never changes here.
+__device__ __forceinline__ void resolve_positions(float v, unsigned int pos, float mn, float mx, unsigned long long* keys2) {
+    if (v == mn) atomicMin(keys2, min_key(v, pos));
+    if (v == mx) atomicMin(keys2 + 1, max_key(v, pos));
+}
+
 __global__ void normalize_kernel(const float* __restrict__ x, float* __restrict__ out,
-                                 const unsigned long long* __restrict__ keys, long long elems, float scale) {
+                                 unsigned long long* __restrict__ keys, long long elems, float scale) {
     const int c = blockIdx.y;
     float mn, mx;
     unsigned int p0, p1;
     key_min_value(keys[2 * c], mn, p0);
     key_max_value(keys[2 * c + 1], mx, p1);
+    // always on: deciding from the keys' current state would let a block that starts late skip its part of the volume
+    // and lose the lowest-position tie rule; the two compares per value are free in a pass bound by its memory traffic
+    constexpr bool resolve = true;
     const float den = __fadd_rn(__fsub_rn(mx, mn), 1e-15f);
     const float* xc = x + (size_t)c * elems;
     float* oc = out + (size_t)c * elems;
     const long long n4 = elems / 4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 v = __ldg(reinterpret_cast<const float4*>(xc) + i);
+        if (resolve) {
+            resolve_positions(v.x, (unsigned int)(4 * i), mn, mx, keys + 2 * c);
+            resolve_positions(v.y, (unsigned int)(4 * i + 1), mn, mx, keys + 2 * c);
+            resolve_positions(v.z, (unsigned int)(4 * i + 2), mn, mx, keys + 2 * c);
+            resolve_positions(v.w, (unsigned int)(4 * i + 3), mn, mx, keys + 2 * c);
+        }
         v.x = __fmul_rn(__fdiv_rn(__fsub_rn(v.x, mn), den), scale);
         v.y = __fmul_rn(__fdiv_rn(__fsub_rn(v.y, mn), den), scale);
         v.z = __fmul_rn(__fdiv_rn(__fsub_rn(v.z, mn), den), scale);
@@ -105,8 +122,10 @@ __global__ void normalize_kernel(const float* __restrict__ x, float* __restrict_
         reinterpret_cast<float4*>(oc)[i] = v;
     }
     if (blockIdx.x == 0)
-        for (long long i = n4 * 4 + threadIdx.x; i < elems; i += blockDim.x)
+        for (long long i = n4 * 4 + threadIdx.x; i < elems; i += blockDim.x) {
+            if (resolve) resolve_positions(xc[i], (unsigned int)i, mn, mx, keys + 2 * c);
             oc[i] = __fmul_rn(__fdiv_rn(__fsub_rn(xc[i], mn), den), scale);
+        }
 }
 
 // Backward.  With m = min, R = max - min, s = scale / (R + eps):  out_i = s (x_i - m), so

@@ -20,7 +20,7 @@
 
 namespace lct {
 
-constexpr int kEllStride = 32;                        // == TimeTile::CT (static_assert in the kernels)
+constexpr int kEllStride = 32;                        // default tile width; build_tables takes the kernel's own (TimeTile<M>::CT)
 
 struct EllRow { int32_t offset; float w[3]; };       // 16 bytes, loaded as float4
 // The time-forward kernel consumes rows in pairs (2p, 2p+1) -- the real and imaginary input of the packed-real
@@ -43,12 +43,14 @@ struct HostTables {
 };
 
 inline std::vector<EllRow> make_ell(int M, const std::vector<int32_t>& rowptr, const std::vector<int32_t>& start,
-                                    const std::vector<float>& vals) {
+                                    const std::vector<float>& vals, int stride = kEllStride) {
     std::vector<EllRow> ell(M);
     for (int i = 0; i < M; ++i) {
         const int len = rowptr[i + 1] - rowptr[i];
-        // the low bits of the offset (free: it is a multiple of kEllStride) carry the number of entries past the third
-        ell[i].offset = (len > 0 ? start[i] : 0) * kEllStride + (len > 3 ? len - 3 : 0);
+        // the low bits of the offset (free: it is a multiple of the tile width) carry the number of entries past the
+        // third, saturating at stride - 1 (the kernel then takes the true length from the CSR row pointers)
+        const int extra = len > 3 ? len - 3 : 0;
+        ell[i].offset = (len > 0 ? start[i] : 0) * stride + (extra < stride - 1 ? extra : stride - 1);
         for (int e = 0; e < 3; ++e) ell[i].w[e] = (e < len) ? vals[rowptr[i] + e] : 0.0f;
     }
     return ell;
@@ -56,14 +58,14 @@ inline std::vector<EllRow> make_ell(int M, const std::vector<int32_t>& rowptr, c
 
 // Pair records for pairs >= long_pairs (earlier pairs are zero-filled: the kernel takes the row records for them).
 inline std::vector<PairRow> make_pairs(int M, const std::vector<int32_t>& rowptr, const std::vector<int32_t>& start,
-                                       const std::vector<float>& vals, int long_pairs) {
+                                       const std::vector<float>& vals, int long_pairs, int stride = kEllStride) {
     std::vector<PairRow> pr(M / 2);
     std::memset(pr.data(), 0, sizeof(PairRow) * pr.size());
     for (int p = long_pairs; p < M / 2; ++p) {
         const int r0 = 2 * p, r1 = 2 * p + 1;
         const int l0 = rowptr[r0 + 1] - rowptr[r0], l1 = rowptr[r1 + 1] - rowptr[r1];
         const int u = l0 > 0 ? (l1 > 0 ? (start[r0] < start[r1] ? start[r0] : start[r1]) : start[r0]) : (l1 > 0 ? start[r1] : 0);
-        pr[p].offset = u * kEllStride;
+        pr[p].offset = u * stride;
         for (int e = 0; e < l0; ++e) pr[p].a[start[r0] + e - u] = vals[rowptr[r0] + e];
         for (int e = 0; e < l1; ++e) pr[p].b[start[r1] + e - u] = vals[rowptr[r1] + e];
     }
@@ -72,7 +74,8 @@ inline std::vector<PairRow> make_pairs(int M, const std::vector<int32_t>& rowptr
 
 // Returns "" on success, otherwise a description of what is wrong with the operator.
 inline std::string build_tables(int M, const int32_t* rowptr, const int32_t* colidx, const float* vals,
-                                const float* falloff /* M or null */, int tail_rows, HostTables& t, int long_pairs = -1) {
+                                const float* falloff /* M or null */, int tail_rows, HostTables& t, int long_pairs = -1,
+                                int stride = kEllStride /* columns per time tile: TimeTile<M>::CT */) {
     if (long_pairs < 0) long_pairs = M / 2;               // no pair records wanted
     t.M = M;
     if (rowptr[0] != 0) return "CSR row pointers must start at 0";
@@ -97,7 +100,6 @@ inline std::string build_tables(int M, const int32_t* rowptr, const int32_t* col
     for (int i = 0; i < M; ++i) {
         if (rowptr[i + 1] - rowptr[i] > 3 && i >= tail_rows)
             return "operator rows with more than 3 entries must be among the first " + std::to_string(tail_rows) + " rows";
-        if (rowptr[i + 1] - rowptr[i] - 3 >= kEllStride) return "operator rows must have fewer than " + std::to_string(kEllStride + 3) + " entries";
         if (t_count[i] > 3) return "operator columns must have at most 3 entries";
     }
     for (int p = long_pairs; p < M / 2; ++p) {
@@ -113,10 +115,10 @@ inline std::string build_tables(int M, const int32_t* rowptr, const int32_t* col
     t.mtx_vals.assign(vals, vals + nnz);
     t.mtx_vals_falloff.resize(nnz);
     for (int e = 0; e < nnz; ++e) t.mtx_vals_falloff[e] = vals[e] * fall[colidx[e]];   // x*gridz^p (tflct.py:123-127)
-    t.mtx_ell = make_ell(M, t.mtx_rowptr, start, t.mtx_vals);
-    t.mtx_ell_falloff = make_ell(M, t.mtx_rowptr, start, t.mtx_vals_falloff);
-    t.mtx_pair = make_pairs(M, t.mtx_rowptr, start, t.mtx_vals, long_pairs);
-    t.mtx_pair_falloff = make_pairs(M, t.mtx_rowptr, start, t.mtx_vals_falloff, long_pairs);
+    t.mtx_ell = make_ell(M, t.mtx_rowptr, start, t.mtx_vals, stride);
+    t.mtx_ell_falloff = make_ell(M, t.mtx_rowptr, start, t.mtx_vals_falloff, stride);
+    t.mtx_pair = make_pairs(M, t.mtx_rowptr, start, t.mtx_vals, long_pairs, stride);
+    t.mtx_pair_falloff = make_pairs(M, t.mtx_rowptr, start, t.mtx_vals_falloff, long_pairs, stride);
 
     // transpose: mtxi = mtx^T (helper.py:61)
     t.mtxi_rowptr.assign(M + 1, 0);
@@ -131,8 +133,8 @@ inline std::string build_tables(int M, const int32_t* rowptr, const int32_t* col
             t.mtxi_vals_falloff[dst] = vals[e] * fall[j];      // backward: falloff applied to the output bin
         }
     for (int j = 0; j < M; ++j) if (t_count[j] == 0) t_start[j] = 0;
-    t.mtxi_ell = make_ell(M, t.mtxi_rowptr, t_start, t.mtxi_vals);
-    t.mtxi_ell_falloff = make_ell(M, t.mtxi_rowptr, t_start, t.mtxi_vals_falloff);
+    t.mtxi_ell = make_ell(M, t.mtxi_rowptr, t_start, t.mtxi_vals, stride);
+    t.mtxi_ell_falloff = make_ell(M, t.mtxi_rowptr, t_start, t.mtxi_vals_falloff, stride);
     return "";
 }
 

@@ -121,14 +121,17 @@ int lct_backward(const lct_plan* plan, const float* gy, const int32_t* tbe, cons
  * NlosPose.py:54):  out = (x - min) / (max(x - min) + 1e-15) * scale  per channel of `elems` values.
  * min / max travel as two 64-bit keys per channel ({value, position}, device memory, 16 bytes per
  * channel).  lct_forward_minmax is lct_forward that also reduces the keys of the volume it writes
- * (in its last kernel, while the values are in registers); lct_minmax computes them for any tensor.
+ * (in its last kernel, while the values are in registers) -- values only: the position halves of its
+ * keys read "unknown" (0xffffffff) until lct_normalize_feature, which sees every value anyway, has filled
+ * them in (it updates the key buffer in place; a NaN or infinity in the volume makes lct_forward_minmax
+ * resolve the positions itself).  lct_minmax computes complete keys for any tensor.
  * The backward pass needs `sums`: 16 bytes of device scratch per channel.
  */
 int lct_forward_minmax(const lct_plan* plan, const float* x, const int32_t* tbe, const int32_t* ten,
                        int32_t B, int32_t D, int32_t Tin, float* y, void* minmax_keys,
                        void* workspace, size_t workspace_bytes, void* stream);
 int lct_minmax(const float* x, int32_t channels, int64_t elems, void* minmax_keys, void* stream);
-int lct_normalize_feature(const float* x, const void* minmax_keys, float* out, int32_t channels, int64_t elems,
+int lct_normalize_feature(const float* x, void* minmax_keys, float* out, int32_t channels, int64_t elems,
                           float scale, void* stream);
 int lct_normalize_feature_backward(const float* x, const float* gout, const void* minmax_keys, float* gx,
                                    void* sums, int32_t channels, int64_t elems, float scale, void* stream);

@@ -126,7 +126,7 @@ int lct_emu_run(int M, int N, int C, int D, int Tin, int be_uniform, const int* 
                 const int* mtx_rowptr, const int* mtx_colidx, const float* mtx_vals, const float* falloff,
                 const float* filt, const float* filt_plane, int backward, int mask, int filt_sym) {
     lct::HostTables ht;
-    if (!lct::build_tables(M, mtx_rowptr, mtx_colidx, mtx_vals, falloff, lct::time_tail_rows(M), ht, lct::time_long_pairs(M)).empty()) return 100;
+    if (!lct::build_tables(M, mtx_rowptr, mtx_colidx, mtx_vals, falloff, lct::time_tail_rows(M), ht, lct::time_long_pairs(M), lct::time_tile_columns(M)).empty()) return 100;
     auto band = [](const std::vector<lct::EllRow>& e, const std::vector<int32_t>& rp, const std::vector<float>& v,
                    const std::vector<lct::PairRow>* pr = nullptr) {
         return lct::BandTable{reinterpret_cast<const float4*>(e.data()), rp.data(), v.data(),

@@ -15,7 +15,7 @@ from bench import WORKLOADS, bin_len_for, chain_bytes, stage_bytes, measured_pea
 
 
 def main():
-    names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["cfg2"]
+    names = [a for a in sys.argv[1:] if a in WORKLOADS or a.startswith("custom:")] or ["cfg2"]     # custom:B,M,N
     bwd = "--bwd" in sys.argv
     reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 40
     dev = torch.device("cuda", 0)
@@ -23,7 +23,7 @@ def main():
     peak = measured_peak()[0]
     tag = os.path.basename(os.environ.get("HIDDENPOSE_LCT_LIB", "in-tree"))
     for name in names:
-        B, M, N, _ = WORKLOADS[name]
+        B, M, N = [int(v) for v in name[7:].split(",")] if name.startswith("custom:") else WORKLOADS[name][:3]
         fuse = "--fp" in sys.argv
         layer = hp.lct(spatial=N, crop=M, bin_len=bin_len_for(M))
         layer.todev(dev, 1)
