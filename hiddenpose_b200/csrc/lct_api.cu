@@ -89,7 +89,6 @@ struct GpuLauncher {
     void mark(int i) {
         if (events && err == cudaSuccess) err = cudaEventRecord((cudaEvent_t)events[i], stream);
     }
-    int launch_mid_l2(const lct::Params& p, float2* slabs, int blocks);
     template <class K> int launch(const lct::Params& p) {
         static std::atomic<bool> attr_set[kMaxDevices] = {};
         auto kern = lct::lct_kernel<K>;
@@ -115,29 +114,6 @@ struct GpuLauncher {
     }
 };
 
-template <int N> int launch_mid_l2_n(GpuLauncher& l, const lct::Params& p, float2* slabs, int blocks) {
-    using F = lct::MidL2<N>;
-    static std::atomic<bool> attr_set[kMaxDevices] = {};
-    auto kern = lct::mid_l2_kernel<N>;
-    if (!attr_set[l.device]) {
-        if (F::kSmem > 48 * 1024) {
-            l.err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F::kSmem);
-            if (l.err != cudaSuccess) return 1;
-        }
-        l.err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (l.err != cudaSuccess) return 1;
-        attr_set[l.device] = true;
-    }
-    lct::Params q = p;
-    q.ahead = 0;
-    q.stagger_ns = 0;
-    const int resident = (l.sms > 0 ? l.sms : 148) * F::kMinBlocks;
-    const int grid = F::grid(q, resident < blocks ? resident : blocks);
-    kern<<<grid, F::kThreads, F::kSmem, l.stream>>>(q, slabs);
-    l.err = cudaGetLastError();
-    return l.err == cudaSuccess ? 0 : 1;
-}
-
 template <class T> int to_device(const T* host, size_t count, T** out) {
     LCT_CUDA(cudaMalloc((void**)out, count * sizeof(T)));
     LCT_CUDA(cudaMemcpy(*out, host, count * sizeof(T), cudaMemcpyHostToDevice));
@@ -151,11 +127,6 @@ constexpr int kWindowChunk = 256;
 struct WindowChunk { int v[kWindowChunk]; };
 __global__ void set_windows_kernel(int* dst, const WindowChunk w, int n) {
     if ((int)threadIdx.x < n) dst[threadIdx.x] = w.v[threadIdx.x];
-}
-
-int GpuLauncher::launch_mid_l2(const lct::Params& p, float2* slabs, int blocks) {
-    if (p.N == 128) return launch_mid_l2_n<128>(*this, p, slabs, blocks);
-    return -1;
 }
 
 __global__ void scale_filter_kernel(float2* f, size_t n, float s) {
@@ -252,17 +223,11 @@ struct lct_plan {
     float2* filt = nullptr;         // natural layout (unfused K3) or, with filt_sym, its quarter (M+1, N+1, N+1); or
     float2* filt_plane = nullptr;   // [kt][kw][plane row] (plane-fused kernel); exactly one of the two is set
     int filt_sym = 0;               // lct::FilterLayout of `filt`
-    bool l2_fused = false;          // K2 + K3 + K4 run as one kernel with the plane resident in L2 (lct::MidL2, N = 128)
-    int l2_blocks = 0;              // slabs per channel group = the most blocks that kernel runs
     bool fused() const { return filt_plane != nullptr; }
-    // S1 (C, M+1, N, N) c64, plus S2 (C, M+1, 2N, N) c64 when the middle stages run as three kernels
-    size_t per_channel_bytes() const { return (size_t)(M + 1) * N * N * sizeof(float2) * ((fused() || l2_fused) ? 1 : 3); }
-    // fixed part of the workspace: the window table, then (L2 fusion) one plane slab per block and channel group
-    size_t slab_bytes() const { return l2_fused ? (size_t)l2_blocks * 2 * N * N * sizeof(float2) : 0; }
-    size_t header_bytes() const { return kHeaderAlign * 16 + slab_bytes() * (size_t)groups; }
-    lct::ChainTables tables(float2* slabs = nullptr) const {
-        return lct::ChainTables{mtx_falloff.view(), mtx.view(), mtxi.view(), mtxi_falloff.view(), filt, filt_plane, filt_sym,
-                                slabs, l2_blocks};
+    // S1 (C, M+1, N, N) c64, plus S2 (C, M+1, 2N, N) c64 when the middle stages are not fused
+    size_t per_channel_bytes() const { return (size_t)(M + 1) * N * N * sizeof(float2) * (fused() ? 1 : 3); }
+    lct::ChainTables tables() const {
+        return lct::ChainTables{mtx_falloff.view(), mtx.view(), mtxi.view(), mtxi_falloff.view(), filt, filt_plane, filt_sym};
     }
 };
 
@@ -392,15 +357,7 @@ int lct_plan_create(const lct_desc* d, lct_plan** out) {
     const float scale = 1.0f / (8.0f * (float)M * (float)N * (float)N);
     const bool fused = lct::plane_fusable(N) && !(d->reserved & LCT_FLAG_NO_PLANE_FUSION);
     float2** slot = fused ? &p->filt_plane : &p->filt;
-    {
-        const char* env = std::getenv("LCT_MID_L2");
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->device);
-        p->l2_fused = !fused && lct::plane_l2_fusable(N) && !(d->reserved & LCT_FLAG_NO_PLANE_FUSION) && !(env && std::atoi(env) == 0);
-        p->l2_blocks = sms * 2;
-    }
-    // the L2-resident fusion re-reads the filter for every plane, from L2: it takes whole rows (no per-value twiddle)
-    const bool allow_sym = !fused && !p->l2_fused && !(d->reserved & LCT_FLAG_FULL_FILTER);
+    const bool allow_sym = !fused && !(d->reserved & LCT_FLAG_FULL_FILTER);
     // which part of a symmetric filter the unfused column kernel of this size wants (lct_kernels.cuh, Params::filt_sym)
     const int sym_layout = N >= 256 ? lct::kFilterHalfRows : lct::kFilterQuarter;
     const int sym_pitch = sym_layout == lct::kFilterHalfRows ? 2 * N : N + 1;
@@ -489,7 +446,7 @@ int32_t lct_plan_spatial(const lct_plan* plan) { return plan ? plan->N : 0; }
 
 size_t lct_plan_workspace_bytes(const lct_plan* plan, int32_t channels) {
     if (!plan || channels <= 0) return 0;
-    return plan->header_bytes() + plan->per_channel_bytes() * (size_t)channels;
+    return kHeaderAlign * 16 + plan->per_channel_bytes() * (size_t)channels;
 }
 
 static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const int32_t* ten,
@@ -505,9 +462,9 @@ static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const 
     }
     const int M = plan->M, N = plan->N;
     const long long C = (long long)B * D;
-    const size_t header = plan->header_bytes();
+    const size_t header = kHeaderAlign * 16;
     if (ws_bytes < header + plan->per_channel_bytes()) return fail(LCT_ERR_WORKSPACE, "workspace too small");
-    if (!uniform && (size_t)B * sizeof(int) > kHeaderAlign * 16) return fail(LCT_ERR_INVALID, "too many distinct windows (batch > 1024)");
+    if (!uniform && (size_t)B * sizeof(int) > header) return fail(LCT_ERR_INVALID, "too many distinct windows (batch > 1024)");
     long long chunk = (long long)((ws_bytes - header) / plan->per_channel_bytes());
     const long long grid_cap = 65535 / (M + 1);
     if (chunk > grid_cap) chunk = grid_cap;
@@ -534,9 +491,7 @@ static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const 
     const size_t out_stride = (size_t)(backward ? Tin : M) * N * N;
     if (events && chunk < C) return fail(LCT_ERR_WORKSPACE, "stage events need a workspace for the whole batch");
     if (minmax_keys) LCT_CUDA(cudaMemsetAsync(minmax_keys, 0xFF, (size_t)C * 2 * sizeof(unsigned long long), stream));
-    float2* slabs = plan->l2_fused ? reinterpret_cast<float2*>(base + kHeaderAlign * 16) : nullptr;
-    const size_t slab_stride = plan->slab_bytes() / sizeof(float2);         // per channel group
-    const lct::ChainTables t = plan->tables(slabs);
+    const lct::ChainTables t = plan->tables();
     if (plan->groups > 1 && chunk >= C && C >= 2 && !events) {     // per-kernel events need the single-stream order
         // one batch: split the channels into groups, each an independent chain on its own stream
         std::lock_guard<std::mutex> lock(plan->side_mutex);
@@ -558,9 +513,7 @@ static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const 
             GpuLauncher lg{sg, plan->device};
             lg.prefetch_ahead = plan->prefetch_ahead;
             lg.stagger_ns = plan->stagger_ns; lg.sms = plan->sms;
-            lct::ChainTables tg = t;
-            if (slabs) tg.l2_slabs = slabs + (size_t)g * slab_stride;         // concurrent groups: separate slabs
-            const int rc = lct::run_chain(lg, tg, M, N, (int)(c1 - c0), D, Tin, tbe[0], be_dev, (int)c0,
+            const int rc = lct::run_chain(lg, t, M, N, (int)(c1 - c0), D, Tin, tbe[0], be_dev, (int)c0,
                                           in + (size_t)c0 * in_stride, out + (size_t)c0 * out_stride,
                                           s1 + (size_t)c0 * (M + 1) * N * N, s2 + (size_t)c0 * (M + 1) * 2 * N * N, backward,
                                           lct::kStageAll, minmax_keys);

@@ -115,144 +115,6 @@ template <int N, class Launcher> int launch_plane(const Params& p, Launcher& l) 
     else return -1;
 }
 
-// ---------------------------------------------------------------------------
-// K2 + K3 + K4 with the zero-extended plane resident in L2 (N = 128: the 2N x N c64 plane is 256 KB -- too large for
-// shared memory, small enough that every resident block's plane stays in the 126 MB L2).  A persistent block takes one
-// (c, kt) plane at a time through all three passes: H forward from S1 into its own scratch slab, the W pass in place
-// on the slab, H inverse from the slab back over the plane in S1.  The slab is rewritten for every plane the block
-// processes, so its lines stay dirty-and-hot in L2 and never have to reach DRAM: per plane the kernel moves S1 in and
-// out once (16 B per spectrum element, as the plane-resident kernel does) plus the filter, instead of the 80 B of the
-// three separate passes.  The passes are the very phase functions of RowFwd / ColFilter / RowInv, pointed at the slab.
-// ---------------------------------------------------------------------------
-constexpr bool plane_l2_fusable(int N) { return N == 128; }
-template <int N_> struct MidL2 {
-    static constexpr int N = N_, L = 2 * N, CT = 16;
-    using K2 = RowFwd<typename RowFwdPlan<L>::type, CT>;
-    using K3 = ColFilter<typename LinePlan<L>::type, LineRows<N>::RB, false>;
-    using K4 = RowInv<typename RowInvPlan<L>::type, CT>;
-    static constexpr int kThreads = K3::kThreads, RB = K3::RB;
-    static_assert(K2::kThreads == kThreads && K4::kThreads == kThreads, "the three passes share one block shape");
-    static_assert(K2::TwS::kBytes == 0 && K4::TwS::kBytes == 0, "only the W pass keeps a twiddle table in shared memory");
-    static constexpr size_t kTw = K3::TwL::kBytes;                          // at offset 0, where TwLine::at looks for it
-    static constexpr size_t kBody = (K2::kSmem > K3::kSmem - kTw ? K2::kSmem : K3::kSmem - kTw) > K4::kSmem
-                                        ? (K2::kSmem > K3::kSmem - kTw ? K2::kSmem : K3::kSmem - kTw) : K4::kSmem;
-    static constexpr size_t kSmem = kTw + kBody;
-    static constexpr int kMinBlocks = 2;
-    static constexpr size_t kSlab = (size_t)L * N;                           // float2 per block
-    static int grid(const Params& p, int resident) { const long long planes = (long long)p.C * (p.M + 1); return (int)(planes < resident ? planes : resident); }
-    // plane index -> (channel, kt): channel fastest, so the C planes that share a filter plane run close together
-    LCT_HD static void split(const Params& p, int plane, int& c, int& kt) { c = plane % p.C; kt = plane / p.C; }
-    LCT_HD static Params for_rows(const Params& p, int c, int kt, float2* slab) {          // K2 / K4: by = 0
-        Params q = p;
-        q.ahead = 0;
-        q.s1 = p.s1 + ((size_t)c * (p.M + 1) + kt) * N * N;
-        q.s2 = slab;
-        return q;
-    }
-    LCT_HD static Params for_cols(const Params& p, int kt, float2* slab) {                  // K3: by = kt, it = 0
-        Params q = p;
-        q.ahead = 0;
-        q.C = 1;
-        q.s2 = slab - (size_t)kt * L * N;            // ColFilter addresses row (kt * L + kh) of channel `it`
-        return q;
-    }
-};
-
-#ifndef LCT_EMULATE
-template <int N> __global__ void __launch_bounds__(MidL2<N>::kThreads, MidL2<N>::kMinBlocks)
-mid_l2_kernel(const Params p, float2* __restrict__ slabs) {
-    using F = MidL2<N>;
-    using P2 = typename F::K2::Plan_;
-    using P4 = typename F::K4::Plan_;
-    constexpr int L = F::L, CT = F::CT, NT = N / CT;
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int tid = threadIdx.x;
-    typename F::K3::Regs r3;
-    F::K3::prologue(p, r3, smem, tid, 0, 0);
-    __syncthreads();
-    float2* slab = slabs + (size_t)blockIdx.x * F::kSlab;
-    float2* zs = reinterpret_cast<float2*>(smem + F::kTw);
-    const int col = tid % CT, tau = line_thread<CT>(tid);
-    const int planes = p.C * (p.M + 1);
-    for (int plane = blockIdx.x; plane < planes; plane += gridDim.x) {
-        int c, kt;
-        F::split(p, plane, c, kt);
-        const Params qc = F::for_cols(p, kt, slab);
-        float2* s1 = p.s1 + ((size_t)c * (p.M + 1) + kt) * N * N;
-        {   // ask L2 for the S1 plane this block takes next while this one is being worked on
-            const int next = plane + gridDim.x;
-            if (next < planes) {
-                int nc, nkt;
-                F::split(p, next, nc, nkt);
-                const char* np = reinterpret_cast<const char*>(p.s1 + ((size_t)nc * (p.M + 1) + nkt) * N * N);
-                for (int i = tid; i < N * N * (int)sizeof(float2) / 128; i += F::kThreads) prefetch_l2(np + (size_t)i * 128);
-            }
-        }
-        // ---- H forward: S1 plane -> slab, CT columns at a time; the next tile's inputs are loaded while this one is transformed
-        static_assert(P2::L / P2::radix(0) == P2::TL, "one stage-0 butterfly per thread");
-        constexpr int kIn = P2::radix(0) / 2;
-        float2 nxt[kIn];
-        auto load_fwd = [&](int tile) {
-            const float2* src = s1 + tile * CT + col;
-            LCT_UNROLL
-            for (int q = 0; q < kIn; ++q) nxt[q] = src[(size_t)(tau + q * P2::st(0)) * N];
-        };
-#ifndef LCT_MIDL2_SKIP
-#define LCT_MIDL2_SKIP 0          // timing-only builds: 1 = no H passes, 2 = no W pass (results are wrong)
-#endif
-        load_fwd(0);
-        for (int tile = 0; tile < ((LCT_MIDL2_SKIP & 1) ? 0 : NT); ++tile) {
-            float2 cur[kIn];
-            LCT_UNROLL
-            for (int q = 0; q < kIn; ++q) cur[q] = nxt[q];
-            if (tile + 1 < NT) load_fwd(tile + 1);
-            fwd_stage<P2, 0, true, TwNone>(tau,
-                [&](int, int slot) { return cur[slot]; },
-                [&](int pos, int, float2 v) { zs[pos * CT + col] = v; });
-            __syncthreads();
-            float2* dst = slab + tile * CT + col;
-            fwd_stage<P2, 1, false, TwNone>(tau,
-                [&](int pos, int) { return zs[pos * CT + col]; },
-                [&](int pos, int slot, float2 v) { dst[(size_t)P2::template freq_of<1>(pos, slot) * N] = v; });
-            __syncthreads();                                             // also orders the slab writes before the reads below
-        }
-        // ---- W pass, in place on the slab (warp-synchronous: ColFilter's own phases)
-        for (int rb = 0; rb < ((LCT_MIDL2_SKIP & 2) ? 0 : L / F::RB); ++rb) {
-            F::K3::template phase<0>(qc, r3, smem, tid, rb, kt, 0);
-            __syncwarp();
-            F::K3::template phase<1>(qc, r3, smem, tid, rb, kt, 0);
-            __syncwarp();
-            F::K3::template phase<2>(qc, r3, smem, tid, rb, kt, 0);
-            __syncwarp();
-        }
-        __syncthreads();
-        // ---- H inverse: slab -> S1 plane, again one tile ahead in registers
-        static_assert(P4::L / P4::radix(1) == P4::TL, "one stage-1 butterfly per thread");
-        float2 nin[P4::E];
-        auto load_inv = [&](int tile) {
-            const float2* src = slab + tile * CT + col;
-            for_each_slot<P4, 1>(tau, [&](int pos, int slot) { nin[slot] = src[(size_t)P4::template freq_of<1>(pos, slot) * N]; });
-        };
-        load_inv(0);
-        for (int tile = 0; tile < ((LCT_MIDL2_SKIP & 1) ? 0 : NT); ++tile) {
-            float2 cin[P4::E];
-            LCT_UNROLL
-            for (int q = 0; q < P4::E; ++q) cin[q] = nin[q];
-            if (tile + 1 < NT) load_inv(tile + 1);
-            inv_stage<P4, 1, false, TwNone>(tau,
-                [&](int, int slot) { return cin[slot]; },
-                [&](int pos, int, float2 v) { zs[pos * CT + col] = v; });
-            __syncthreads();
-            float2* dst = s1 + tile * CT + col;
-            inv_stage<P4, 0, true, TwNone>(tau,
-                [&](int pos, int) { return zs[pos * CT + col]; },
-                [&](int pos, int, float2 v) { dst[(size_t)pos * N] = v; });
-            __syncthreads();
-        }
-    }
-}
-#endif
-
 #define LCT_SWITCH_M(M, CALL)                                   \
     switch (M) {                                                \
         case 32:  { constexpr int kM = 32;  rc = CALL; } break; \
@@ -299,8 +161,6 @@ struct ChainTables {
     const float2* filt;         // (M+1, 2N, 2N) natural order -- or its (M+1, N+1, N+1) quarter -- for K3 (null if fused)
     const float2* filt_plane;   // (M+1, 2N kw, 2N plane rows), for PlaneFilter   (null if not fused)
     int filt_sym;               // FilterLayout of filt (Params::filt_sym)
-    float2* l2_slabs = nullptr; // per-block planes of the L2-resident fusion of K2 + K3 + K4 (MidL2), or null
-    int l2_blocks = 0;          // how many slabs there are (= the most blocks that kernel may run)
 };
 
 // Runs the stages selected in `mask` (all five for a real call).
@@ -332,12 +192,6 @@ int run_chain(Launcher& l, const ChainTables& t, int M, int N, int C, int D, int
     if ((mask & kMiddle) == kMiddle && t.filt_plane) {
         p.filt = t.filt_plane;
         LCT_SWITCH_N(N, (launch_plane<kN>(p, l)));
-        if (rc) return rc;
-        l.mark(2); l.mark(3);
-        mask &= ~kMiddle;
-    }
-    if ((mask & kMiddle) == kMiddle && t.l2_slabs && plane_l2_fusable(N) && !t.filt_sym) {
-        rc = l.launch_mid_l2(p, t.l2_slabs, t.l2_blocks);
         if (rc) return rc;
         l.mark(2); l.mark(3);
         mask &= ~kMiddle;

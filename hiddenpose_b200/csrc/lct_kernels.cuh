@@ -787,7 +787,6 @@ template <class P, int CT_> struct TimeInv {
 // K2: zero-extended forward FFT along H.  One block = one (c, kt) plane x CT columns.
 // ---------------------------------------------------------------------------
 template <class P, int CT_> struct RowFwd {
-    using Plan_ = P;
     using TwS = TwNone;                        // constant-bank twiddles (a block-local table measured slower here)
     static constexpr int L = P::L, N = L / 2, CT = CT_, kThreads = P::TL * CT;
     static constexpr int kPhases = P::S;
@@ -840,7 +839,6 @@ template <class P, int CT_> struct RowFwd {
 // K4: inverse FFT along H, keep h < N.
 // ---------------------------------------------------------------------------
 template <class P, int CT_> struct RowInv {
-    using Plan_ = P;
     using TwS = TwNone;                        // constant-bank twiddles (a block-local table measured slower here)
     static constexpr int L = P::L, N = L / 2, CT = CT_, kThreads = P::TL * CT;
     static constexpr int kPhases = P::S;

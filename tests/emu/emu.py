@@ -55,7 +55,7 @@ class EmuPlan:
         self.filt_plane = (np.ascontiguousarray(self.filt[:, kh, :].reshape(M + 1, L, N, 2).transpose(0, 2, 1, 3))
                            if N <= 64 else None)
 
-    def run(self, inp, D, Tin, be, backward=False, mask=31, reverse=False, s1=None, s2=None, fused=True, drift=0, sym=False, l2=False):
+    def run(self, inp, D, Tin, be, backward=False, mask=31, reverse=False, s1=None, s2=None, fused=True, drift=0, sym=False):
         M, N = self.M, self.N
         inp = np.ascontiguousarray(inp, dtype=np.float32)
         C = inp.shape[0]
@@ -77,7 +77,7 @@ class EmuPlan:
             _p(self.csr[0], i32), _p(self.csr[1], i32), _p(self.csr[2], f), _p(self.falloff, f),
             _p((self.filt_quarter if sym else self.filt).view(np.float32), f),
             _p(self.filt_plane.view(np.float32), f) if (fused and self.filt_plane is not None) else None,
-            int(backward), int(mask), (2 if self.N >= 256 else 1) if sym else 0, int(l2))
+            int(backward), int(mask), (2 if self.N >= 256 else 1) if sym else 0)
         lib().lct_emu_set_drift(0)
         assert rc == 0, rc
         return out, s1, s2

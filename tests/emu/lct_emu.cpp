@@ -70,62 +70,8 @@ template <class K> void run_phases_drifting(const lct::Params& p, std::vector<ty
     }
 }
 
-template <class K, int PH> void run_all_threads(const lct::Params& p, std::vector<typename K::Regs>& regs, unsigned char* smem,
-                                                int bx, int by, int it) {
-    for (int i = 0; i < K::kThreads; ++i) {
-        const int tid = g_reverse_threads ? K::kThreads - 1 - i : i;
-        K::template phase<PH>(p, regs[tid], smem, tid, bx, by, it);
-    }
-}
-
-// The L2-resident fusion of K2 + K3 + K4 (lct::MidL2, mid_l2_kernel): the same per-plane walk, every barrier-delimited
-// phase stepped over all threads of the block.
-template <int N> int emulate_mid_l2(const lct::Params& p, float2* slabs, int blocks) {
-    using F = lct::MidL2<N>;
-    const int planes = p.C * (p.M + 1);
-    const int nblocks = blocks < planes ? blocks : planes;
-    for (int b = 0; b < nblocks; ++b) {
-        std::vector<unsigned char> smem(F::kSmem + 64);
-        float* f = reinterpret_cast<float*>(smem.data());
-        for (size_t i = 0; i < smem.size() / 4; ++i) f[i] = std::numeric_limits<float>::quiet_NaN();
-        std::memset(smem.data() + F::kSmem, 0xA5, 64);
-        std::vector<typename F::K2::Regs> r2(F::kThreads);
-        std::vector<typename F::K3::Regs> r3(F::kThreads);
-        std::vector<typename F::K4::Regs> r4(F::kThreads);
-        float2* slab = slabs + (size_t)b * F::kSlab;
-        for (int plane = b; plane < planes; plane += nblocks) {
-            int c, kt;
-            F::split(p, plane, c, kt);
-            const lct::Params qr = F::for_rows(p, c, kt, slab);
-            const lct::Params qc = F::for_cols(p, kt, slab);
-            for (int tile = 0; tile < N / F::CT; ++tile) {
-                run_all_threads<typename F::K2, 0>(qr, r2, smem.data() + F::kTw, tile, 0, 0);
-                run_all_threads<typename F::K2, 1>(qr, r2, smem.data() + F::kTw, tile, 0, 0);
-            }
-            for (int rb = 0; rb < F::L / F::RB; ++rb) {
-                run_all_threads<typename F::K3, 0>(qc, r3, smem.data(), rb, kt, 0);
-                run_all_threads<typename F::K3, 1>(qc, r3, smem.data(), rb, kt, 0);
-                run_all_threads<typename F::K3, 2>(qc, r3, smem.data(), rb, kt, 0);
-            }
-            for (int tile = 0; tile < N / F::CT; ++tile) {
-                run_all_threads<typename F::K4, 0>(qr, r4, smem.data() + F::kTw, tile, 0, 0);
-                run_all_threads<typename F::K4, 1>(qr, r4, smem.data() + F::kTw, tile, 0, 0);
-            }
-        }
-        for (int g = 0; g < 64; ++g)
-            if (smem[F::kSmem + g] != 0xA5) return 200;
-    }
-    return 0;
-}
-
 struct EmuLauncher {
     void mark(int) {}
-    int launch_mid_l2(const lct::Params& p0, float2* slabs, int blocks) {
-        lct::Params p = p0;
-        p.ahead = 0;
-        if (p.N == 128) return emulate_mid_l2<128>(p, slabs, blocks);
-        return -1;
-    }
     template <class K> int launch(const lct::Params& p0) {
         lct::Params p = p0;
         p.ahead = 3;                                         // three "resident" blocks: persistent kernels walk several tiles each
@@ -178,7 +124,7 @@ void lct_emu_set_drift(int mode) { g_drift = mode; }
 int lct_emu_run(int M, int N, int C, int D, int Tin, int be_uniform, const int* be,
                 const float* in, float* out, float* s1, float* s2,
                 const int* mtx_rowptr, const int* mtx_colidx, const float* mtx_vals, const float* falloff,
-                const float* filt, const float* filt_plane, int backward, int mask, int filt_sym, int mid_l2) {
+                const float* filt, const float* filt_plane, int backward, int mask, int filt_sym) {
     lct::HostTables ht;
     if (!lct::build_tables(M, mtx_rowptr, mtx_colidx, mtx_vals, falloff, lct::time_tail_rows(M), ht, lct::time_long_pairs(M), lct::time_tile_columns(M)).empty()) return 100;
     auto band = [](const std::vector<lct::EllRow>& e, const std::vector<int32_t>& rp, const std::vector<float>& v,
@@ -190,14 +136,6 @@ int lct_emu_run(int M, int N, int C, int D, int Tin, int be_uniform, const int* 
                        band(ht.mtx_ell, ht.mtx_rowptr, ht.mtx_vals, &ht.mtx_pair),
                        band(ht.mtxi_ell, ht.mtxi_rowptr, ht.mtxi_vals), band(ht.mtxi_ell_falloff, ht.mtxi_rowptr, ht.mtxi_vals_falloff),
                        reinterpret_cast<const float2*>(filt), reinterpret_cast<const float2*>(filt_plane), filt_sym};
-    std::vector<float2> slabs;
-    if (mid_l2 && lct::plane_l2_fusable(N)) {               // three "resident" blocks, slabs poisoned
-        t.l2_blocks = 3;
-        float2 nan2;
-        nan2.x = nan2.y = std::numeric_limits<float>::quiet_NaN();
-        slabs.assign((size_t)t.l2_blocks * 2 * N * N, nan2);
-        t.l2_slabs = slabs.data();
-    }
     EmuLauncher l;
     return lct::run_chain(l, t, M, N, C, D, Tin, be_uniform, be, 0, in, out,
                           reinterpret_cast<float2*>(s1), reinterpret_cast<float2*>(s2), backward != 0, mask);
