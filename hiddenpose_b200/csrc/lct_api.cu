@@ -85,7 +85,6 @@ struct GpuLauncher {
     cudaError_t err = cudaSuccess;
     void* const* events = nullptr;          // optional: 6 cudaEvent_t recorded around the stages
     int prefetch_ahead = 0;                 // SM count when the time kernels should warm L2 for later blocks, else 0
-    int stagger_ns = 0, sms = 0;
     void mark(int i) {
         if (events && err == cudaSuccess) err = cudaEventRecord((cudaEvent_t)events[i], stream);
     }
@@ -104,8 +103,6 @@ struct GpuLauncher {
         }
         lct::Params q = p;
         q.ahead = prefetch_ahead > 0 ? prefetch_ahead * K::kMinBlocks : 0;      // resident blocks of this kernel
-        q.stagger_ns = K::kMinBlocks == 2 ? stagger_ns : 0;
-        q.sms = sms;
         int gx, gy;
         K::grid(q, gx, gy);
         kern<<<dim3(gx, gy), K::kThreads, K::kSmem, stream>>>(q, K::iterations(q));
@@ -196,7 +193,6 @@ struct lct_plan {
     static constexpr int kMaxGroups = 8;
     int groups = 1;
     int prefetch_ahead = 0;                 // SM count, or 0 when LCT_L2_PREFETCH=0 (see GpuLauncher::prefetch_ahead)
-    int stagger_ns = 0, sms = 0;
     // One set of side streams + fork/join events per caller stream (created up front, handed out first come first
     // served): two threads driving the plan on two streams get two sets, so neither waits on the other's kernels.
     // More distinct caller streams than sets share sets round robin -- still correct (every use is ordered by its
@@ -413,9 +409,6 @@ int lct_plan_create(const lct_desc* d, lct_plan** out) {
         int sms = 0;
         if ((!pf || std::atoi(pf) != 0) && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->device) == cudaSuccess)
             p->prefetch_ahead = sms;
-        cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, d->device);
-        const char* sg = std::getenv("LCT_STAGGER_NS");
-        p->stagger_ns = sg ? std::atoi(sg) : 0;
     }
     {
         const char* env = std::getenv("LCT_STREAM_GROUPS");
@@ -512,7 +505,6 @@ static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const 
             }
             GpuLauncher lg{sg, plan->device};
             lg.prefetch_ahead = plan->prefetch_ahead;
-            lg.stagger_ns = plan->stagger_ns; lg.sms = plan->sms;
             const int rc = lct::run_chain(lg, t, M, N, (int)(c1 - c0), D, Tin, tbe[0], be_dev, (int)c0,
                                           in + (size_t)c0 * in_stride, out + (size_t)c0 * out_stride,
                                           s1 + (size_t)c0 * (M + 1) * N * N, s2 + (size_t)c0 * (M + 1) * 2 * N * N, backward,
@@ -533,7 +525,6 @@ static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const 
     GpuLauncher l{stream, plan->device};
     l.events = events;
     l.prefetch_ahead = plan->prefetch_ahead;
-    l.stagger_ns = plan->stagger_ns; l.sms = plan->sms;
     for (long long c0 = 0; c0 < C; c0 += chunk) {
         const int cn = (int)((C - c0 < chunk) ? (C - c0) : chunk);
         const int rc = lct::run_chain(l, t, M, N, cn, D, Tin, tbe[0], be_dev, (int)c0,

@@ -198,9 +198,6 @@ struct Params {
     // time kernels: how many blocks ahead (in launch order) the tile to warm in L2 lies; 0 = no prefetch.
     // The launcher sets it to the number of resident blocks, so the lines arrive about one block life early.
     int ahead;
-    // experiment hook (LCT_STAGGER_NS): blocks of the second residency slot of each SM start this many ns late, so
-    // that co-resident blocks run their memory and compute phases out of step; sms = SM count
-    int stagger_ns, sms;
 };
 
 LCT_DEV void prefetch_l2(const void* ptr) {
@@ -1435,10 +1432,6 @@ template <class K, int PH> struct PhaseLoop {
 template <class K> __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) lct_kernel(const Params p, const int iters) {
     extern __shared__ __align__(16) unsigned char smem[];
     typename K::Regs r;
-    if (p.stagger_ns > 0) {
-        const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x;
-        if (lin >= (unsigned)p.sms && lin < 2u * (unsigned)p.sms) __nanosleep((unsigned)p.stagger_ns);
-    }
     if constexpr (has_prologue<K>::value) {
         K::prologue(p, r, smem, threadIdx.x, blockIdx.x, blockIdx.y);
         __syncthreads();

@@ -1,3 +1,8 @@
+#!/usr/bin/env python
+"""Why bench.py's 20-step mean sat 16 us above the steady-state step (GPU box): prints the per-step CUDA-event times of the
+headline loop with and without the NVML clock sampler, for 20 and 200 steps.  Finding (round 2): the first step after the
+barrier + synchronize takes 300-490 us because the launch queue is empty and the device waits on the host; bench.py now
+queues a ~1 ms memset pre-roll after the barrier."""
 import os, sys, statistics, time
 sys.path.insert(0, '/root/repo')
 import torch

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Small forward+backward sweep for compute-sanitizer (memcheck / racecheck), one tool per GPU call:
     compute-sanitizer --tool memcheck python tools/sanitize_run.py
-Covers the fused plane path (N <= 64), the five-kernel path (N = 128), the parity-split kernels (N = 256), ragged windows, D > 1 and bp."""
+Covers the fused plane path (N <= 64), the five-kernel path (N = 128), the parity-split kernels (N = 256), ragged windows, D > 1 and bp.
+
+NOT RUN SO FAR: compute-sanitizer is closed on this GPU pool (both round-1 attempts came back with the pool's refusal), so the
+sweep is kept for a pool where it is open; the race evidence there is comes from the CPU thread emulator (tests/emu)."""
 import os
 import sys
 
