@@ -161,6 +161,19 @@ static inline int float_bits(float f) { int i; std::memcpy(&i, &f, 4); return i;
 LCT_DEV int float_bits(float f) { return __float_as_int(f); }
 #endif
 
+// The parity-split transforms multiply element n of a line by w_2N^n (forward) or its conjugate (inverse).  A stage-0
+// thread owns n = t + q * st with st = N / R0, so w_2N^n = w_2N^t * w_(2 R0)^q: one table value per thread (`wt`, read once)
+// times a compile-time constant -- instead of one lane-divergent table load per element (those loads were a quarter of
+// the memory instructions of the N = 256 row kernels, whose first stall is the memory-instruction queue).
+#ifndef LCT_SPLIT_TW_CONST
+#define LCT_SPLIT_TW_CONST 1
+#endif
+template <int R0, bool INV> LCT_DEV float2 split_twiddle(float2 a, float2 wt, int q) {
+    static_assert(32 % (2 * R0) == 0, "w_(2 R0)^q must be a 32nd root of unity");
+    const float2 b = INV ? cmulc(a, wt) : cmul(a, wt);
+    return twmul32<INV>(b, q * (32 / (2 * R0)));
+}
+
 struct Params {
     int M, N, C, D;
     // K1 input placement: rows [in_be, in_be+in_T) of the M-bin time axis come from `in`
@@ -931,7 +944,11 @@ template <class P, int CT_> struct RowFwdSplit {
             }
             if (parity == 0)
                 fwd_stage<P, 0, false, TwS>(tau, [&](int pos, int) { return src[(size_t)pos * N]; }, st_s);
-            else
+            else if constexpr (LCT_SPLIT_TW_CONST && P::TL == P::st(0)) {
+                const float2 wt = TwGlobal::get(tau * (kTwN / L));
+                fwd_stage<P, 0, false, TwS>(tau,
+                    [&](int pos, int slot) { return split_twiddle<P::R0, false>(src[(size_t)pos * N], wt, slot % P::R0); }, st_s);
+            } else
                 fwd_stage<P, 0, false, TwS>(tau,
                     [&](int pos, int) { return TwGlobal::mul(src[(size_t)pos * N], pos * (kTwN / L)); }, st_s);
         } else {
@@ -991,10 +1008,15 @@ template <class P, int CT_> struct RowInvSplit {
             const float2* zo = zs + N * CT;
             constexpr int kIters = N * CT / kThreads;
             static_assert(N * CT % kThreads == 0 && kThreads % CT == 0, "the plane tile must divide among the threads");
+            // n = tid / CT + u * kStep: conj(w_2N^n) = conj(w_2N^(tid / CT)) * conj of a compile-time root of unity
+            constexpr int kStep = kThreads / CT;
+            constexpr bool kConstTw = LCT_SPLIT_TW_CONST && (32 * kStep) % L == 0;
+            const float2 wn0 = TwGlobal::get((tid / CT) * (kTwN / L));
             LCT_UNROLL
             for (int u = 0; u < kIters; ++u) {
                 const int i = tid + u * kThreads, n = i / CT, col = i % CT;
-                dst[(size_t)n * N + col] = cadd(zs[i], TwGlobal::mulc(zo[i], n * (kTwN / L)));
+                if constexpr (kConstTw) dst[(size_t)n * N + col] = cadd(zs[i], twmul32<true>(cmulc(zo[i], wn0), u * (32 * kStep / L)));
+                else dst[(size_t)n * N + col] = cadd(zs[i], TwGlobal::mulc(zo[i], n * (kTwN / L)));
             }
         }
     }
@@ -1210,9 +1232,15 @@ template <class P, int RB_, bool SYM = false> struct ColFilterSplit {
             // the even parity's filter values are requested here, a whole stage before their first use: at one channel
             // per launch nothing else hides their latency (it was 22 % of the kernel's stall samples)
             if constexpr (kEarlyFilter) load_filter(p, r, tau, kt, kh, 0);
-            fwd_stage<P, 0, false, TwL>(tau,
-                [&](int pos, int slot) { return TwGlobal::mul(r.in[slot], pos * (kTwN / L)); },
-                [&](int pos, int, float2 v) { zo[padpos(pos)] = v; });
+            if constexpr (LCT_SPLIT_TW_CONST && P::TL == P::st(0)) {
+                const float2 wt = TwGlobal::get(tau * (kTwN / L));
+                fwd_stage<P, 0, false, TwL>(tau,
+                    [&](int, int slot) { return split_twiddle<P::R0, false>(r.in[slot], wt, slot % P::R0); },
+                    [&](int pos, int, float2 v) { zo[padpos(pos)] = v; });
+            } else
+                fwd_stage<P, 0, false, TwL>(tau,
+                    [&](int pos, int slot) { return TwGlobal::mul(r.in[slot], pos * (kTwN / L)); },
+                    [&](int pos, int, float2 v) { zo[padpos(pos)] = v; });
             if (it + 1 < p.C) fetch(row + chan, tau, r);        // next channel's row flies during this one's math
         } else if constexpr (PH == 1) {
             float2 a[P::E];
@@ -1236,9 +1264,15 @@ template <class P, int RB_, bool SYM = false> struct ColFilterSplit {
             inv_stage<P, 0, false, TwL>(tau,
                 [&](int pos, int) { return ze[padpos(pos)]; },
                 [&](int, int slot, float2 v) { ya[slot] = v; });
-            inv_stage<P, 0, false, TwL>(tau,
-                [&](int pos, int) { return zo[padpos(pos)]; },
-                [&](int pos, int slot, float2 v) { row[pos] = cadd(ya[slot], TwGlobal::mulc(v, pos * (kTwN / L))); });
+            if constexpr (LCT_SPLIT_TW_CONST && P::TL == P::st(0)) {
+                const float2 wt = TwGlobal::get(tau * (kTwN / L));
+                inv_stage<P, 0, false, TwL>(tau,
+                    [&](int pos, int) { return zo[padpos(pos)]; },
+                    [&](int pos, int slot, float2 v) { row[pos] = cadd(ya[slot], split_twiddle<P::R0, true>(v, wt, slot % P::R0)); });
+            } else
+                inv_stage<P, 0, false, TwL>(tau,
+                    [&](int pos, int) { return zo[padpos(pos)]; },
+                    [&](int pos, int slot, float2 v) { row[pos] = cadd(ya[slot], TwGlobal::mulc(v, pos * (kTwN / L))); });
         }
     }
 };
@@ -1338,9 +1372,18 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
                 fwd_stage_tw<PWp, 0>(tau, tw,
                     [&](int, int slot) { return in[slot]; },
                     [&](int pos, int, float2 v) { Tr[pos] = v; });
-                fwd_stage_tw<PWp, 0>(tau, tw,
-                    [&](int pos, int slot) { return TwP::mul(in[slot], pos * (kTwN / L)); },
-                    [&](int pos, int, float2 v) { Xr[pos] = v; });
+#ifndef LCT_PLANE_TW_CONST
+#define LCT_PLANE_TW_CONST 1
+#endif
+                if constexpr (LCT_PLANE_TW_CONST && PWp::TL == PWp::st(0)) {
+                    const float2 wt = TwP::get(tau * (kTwN / L));          // w_2N^n = w_2N^tau * (compile-time root)
+                    fwd_stage_tw<PWp, 0>(tau, tw,
+                        [&](int, int slot) { return split_twiddle<PWp::R0, false>(in[slot], wt, slot % PWp::R0); },
+                        [&](int pos, int, float2 v) { Xr[pos] = v; });
+                } else
+                    fwd_stage_tw<PWp, 0>(tau, tw,
+                        [&](int pos, int slot) { return TwP::mul(in[slot], pos * (kTwN / L)); },
+                        [&](int pos, int, float2 v) { Xr[pos] = v; });
 #ifndef LCT_EMULATE
                 {   // pull next phase's filter values from L2 towards L1 while the exchange settles
                     const float4* f = reinterpret_cast<const float4*>(p.filt) + (size_t)kt * N * L + row;
@@ -1377,11 +1420,19 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
                 inv_stage_tw<PWp, 0>(tau, tw,
                     [&](int pos, int) { return Tr[pos]; },
                     [&](int, int slot, float2 v) { ya[slot] = v; });
-                inv_stage_tw<PWp, 0>(tau, tw,
-                    [&](int pos, int) { return Xr[pos]; },
-                    [&](int pos, int slot, float2 v) {
-                        Tr[pos] = cadd(ya[slot], TwP::mulc(v, pos * (kTwN / L)));
-                    });
+                if constexpr (LCT_PLANE_TW_CONST && PWp::TL == PWp::st(0)) {
+                    const float2 wt = TwP::get(tau * (kTwN / L));
+                    inv_stage_tw<PWp, 0>(tau, tw,
+                        [&](int pos, int) { return Xr[pos]; },
+                        [&](int pos, int slot, float2 v) {
+                            Tr[pos] = cadd(ya[slot], split_twiddle<PWp::R0, true>(v, wt, slot % PWp::R0));
+                        });
+                } else
+                    inv_stage_tw<PWp, 0>(tau, tw,
+                        [&](int pos, int) { return Xr[pos]; },
+                        [&](int pos, int slot, float2 v) {
+                            Tr[pos] = cadd(ya[slot], TwP::mulc(v, pos * (kTwN / L)));
+                        });
             }
         } else {
             constexpr int s = PH - kW1;
