@@ -345,6 +345,20 @@ LCT_DEV float2 pair_dot(const float4* pairs, int pair, const float* src) {
     return make_float2(fmaf(a.w, x2, fmaf(a.z, x1, a.y * x0)), fmaf(b.z, x2, fmaf(b.y, x1, b.x * x0)));
 }
 
+// Row j of mtxi = mtx^T (the inverse resampling): its band starts at row floor(j^2 / M) of the volume tile -- the closed
+// form of helper.py:35-69's staircase, checked by build_tables -- so the tile address does not wait on the record load:
+// the three tile loads and the record load issue together (the record -> address -> load chain was the first stall of
+// the gather at 16 warps per SM).  LOGM = log2(M).
+#ifndef LCT_MTXI_CLOSED_FORM
+#define LCT_MTXI_CLOSED_FORM 1
+#endif
+template <int STRIDE, int LOGM>
+LCT_DEV float band_dot_sq(const float4* ell, int j, const float* src) {
+    const float4 e = ell[j];
+    const float* s = src + ((j * j) >> LOGM) * STRIDE;
+    return fmaf(e.w, s[2 * STRIDE], fmaf(e.z, s[STRIDE], e.y * s[0]));
+}
+
 LCT_DEV int window_begin(const Params& p, int c) {
     return p.be_dev ? LCT_LDG(p.be_dev + (p.c_base + c) / p.D) : p.be_uniform;
 }
@@ -746,12 +760,15 @@ template <class P, int CT_> struct TimeInv {
             const float* vc = vol + col;
             const float4* ell = reinterpret_cast<const float4*>(smem + kWork);
             if (p.minmax_keys == nullptr) {
-                const float4* er = ell + be + tau;         // mtxi rows have at most three entries: no tail
+                [[maybe_unused]] const float4* er = ell + be + tau;         // mtxi rows have at most three entries: no tail
 #ifndef LCT_EMULATE
 #pragma unroll 8                                   // full unrolling (16) measured 2 % slower at M = 256
 #endif
                 for (int m = 0; m < M / P::TL; ++m, d += step)
-                    if (tau + m * P::TL < p.out_T) *d = band_dot<false, CT>(p, er, m * P::TL, vc);
+                    if (tau + m * P::TL < p.out_T) {
+                        if constexpr (LCT_MTXI_CLOSED_FORM) *d = band_dot_sq<CT, P::ilog2(M)>(ell, be + tau + m * P::TL, vc);
+                        else *d = band_dot<false, CT>(p, er, m * P::TL, vc);
+                    }
             } else {
                 // Values only (two FMNMX per output): the positions the backward of normalize_feature needs are found by
                 // the normalisation pass itself, which reads every value anyway (lct_normalize.cuh) -- the keys leave
@@ -761,13 +778,15 @@ template <class P, int CT_> struct TimeInv {
                 // or an infinity: one FFMA per output); a poisoned strip redoes its reduction on the integer keys, where
                 // NaN wins both sides as it does in torch.min / torch.max.
                 float mn = kInfinity, mx = -kInfinity, poison = 0.f;
-                const float4* er = ell + be + tau;         // same loop shape as the plain path above
+                [[maybe_unused]] const float4* er = ell + be + tau;         // same loop shape as the plain path above
 #ifndef LCT_EMULATE
 #pragma unroll 8
 #endif
                 for (int m = 0; m < M / P::TL; ++m, d += step)
                     if (tau + m * P::TL < p.out_T) {
-                        const float v = band_dot<false, CT>(p, er, m * P::TL, vc);
+                        float v;
+                        if constexpr (LCT_MTXI_CLOSED_FORM) v = band_dot_sq<CT, P::ilog2(M)>(ell, be + tau + m * P::TL, vc);
+                        else v = band_dot<false, CT>(p, er, m * P::TL, vc);
                         *d = v;
                         poison = fmaf(v, 0.f, poison);
                         mn = fminf(mn, v);

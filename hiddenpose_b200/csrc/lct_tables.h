@@ -132,7 +132,11 @@ inline std::string build_tables(int M, const int32_t* rowptr, const int32_t* col
             t.mtxi_vals[dst] = vals[e];
             t.mtxi_vals_falloff[dst] = vals[e] * fall[j];      // backward: falloff applied to the output bin
         }
-    for (int j = 0; j < M; ++j) if (t_count[j] == 0) t_start[j] = 0;
+    // the inverse gather computes a column's first row instead of reading it (band_dot_sq in lct_kernels.cuh)
+    for (int j = 0; j < M; ++j)
+        if (t_count[j] > 0 && t_start[j] != (int)(((long long)j * j) / M))
+            return "operator column " + std::to_string(j) + " must start at row floor(j^2 / M) (the staircase of helper.py:35-69)";
+    for (int j = 0; j < M; ++j) if (t_count[j] == 0) t_start[j] = (int)(((long long)j * j) / M);
     t.mtxi_ell = make_ell(M, t.mtxi_rowptr, t_start, t.mtxi_vals, stride);
     t.mtxi_ell_falloff = make_ell(M, t.mtxi_rowptr, t_start, t.mtxi_vals_falloff, stride);
     return "";
