@@ -21,6 +21,9 @@
 #include "lct_stencil.cuh"
 #include "lct_tables.h"
 
+#ifndef LCT_DEFAULT_PDL
+#define LCT_DEFAULT_PDL 1
+#endif
 #ifndef LCT_DEFAULT_STREAM_GROUPS
 #define LCT_DEFAULT_STREAM_GROUPS 2
 #endif
@@ -85,6 +88,7 @@ struct GpuLauncher {
     cudaError_t err = cudaSuccess;
     void* const* events = nullptr;          // optional: 6 cudaEvent_t recorded around the stages
     int prefetch_ahead = 0;                 // SM count when the time kernels should warm L2 for later blocks, else 0
+    int pdl = 0;                            // programmatic dependent launch mode (Params::pdl); off while stage events are recorded
     void mark(int i) {
         if (events && err == cudaSuccess) err = cudaEventRecord((cudaEvent_t)events[i], stream);
     }
@@ -105,8 +109,26 @@ struct GpuLauncher {
         q.ahead = prefetch_ahead > 0 ? prefetch_ahead * K::kMinBlocks : 0;      // resident blocks of this kernel
         int gx, gy;
         K::grid(q, gx, gy);
-        kern<<<dim3(gx, gy), K::kThreads, K::kSmem, stream>>>(q, K::iterations(q));
-        err = cudaGetLastError();
+        q.pdl = events ? 0 : pdl;
+        const int iters = K::iterations(q);
+        if (q.pdl) {
+            // the kernel may be scheduled before its predecessor in the stream has drained; it orders itself behind
+            // that kernel's memory with griddepcontrol.wait (lct_kernel)
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(gx, gy);
+            cfg.blockDim = dim3(K::kThreads);
+            cfg.dynamicSmemBytes = K::kSmem;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            err = cudaLaunchKernelEx(&cfg, kern, q, iters);
+        } else {
+            kern<<<dim3(gx, gy), K::kThreads, K::kSmem, stream>>>(q, iters);
+            err = cudaGetLastError();
+        }
         return err == cudaSuccess ? 0 : 1;
     }
 };
@@ -193,6 +215,7 @@ struct lct_plan {
     static constexpr int kMaxGroups = 8;
     int groups = 1;
     int prefetch_ahead = 0;                 // SM count, or 0 when LCT_L2_PREFETCH=0 (see GpuLauncher::prefetch_ahead)
+    int pdl = 0;                            // LCT_PDL: programmatic dependent launch between the kernels of a chain
     // One set of side streams + fork/join events per caller stream (created up front, handed out first come first
     // served): two threads driving the plan on two streams get two sets, so neither waits on the other's kernels.
     // More distinct caller streams than sets share sets round robin -- still correct (every use is ordered by its
@@ -411,8 +434,17 @@ int lct_plan_create(const lct_desc* d, lct_plan** out) {
             p->prefetch_ahead = sms;
     }
     {
+        const char* env = std::getenv("LCT_PDL");
+        p->pdl = (env ? std::atoi(env) : LCT_DEFAULT_PDL) ? 1 : 0;
+    }
+    {
         const char* env = std::getenv("LCT_STREAM_GROUPS");
-        int g = env ? std::atoi(env) : LCT_DEFAULT_STREAM_GROUPS;
+        // Measured with dependent launch on (round 2, one B200): two groups win wherever a kernel of one group has a
+        // tail the other group can fill (8 x 256x64^2: 179 vs 191 us, 16 x 128^3: 740 vs 746, 4 x 256x256^2: 1897 vs
+        // 1950), except at 512x128^2, where the time kernels hold a whole SM per block and two chains only get in
+        // each other's way (2 / 4 / 8 channels: 457 / 815 / 1535 us on one stream against 496 / 845 / 1551 on two)
+        const int by_shape = (p->M == 512 && p->N == 128) ? 1 : LCT_DEFAULT_STREAM_GROUPS;
+        int g = env ? std::atoi(env) : by_shape;
         p->groups = g < 1 ? 1 : (g > lct_plan::kMaxGroups ? lct_plan::kMaxGroups : g);
         for (auto& set : p->sets) {
             for (int i = 1; i < p->groups; ++i) {
@@ -505,6 +537,7 @@ static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const 
             }
             GpuLauncher lg{sg, plan->device};
             lg.prefetch_ahead = plan->prefetch_ahead;
+            lg.pdl = plan->pdl;
             const int rc = lct::run_chain(lg, t, M, N, (int)(c1 - c0), D, Tin, tbe[0], be_dev, (int)c0,
                                           in + (size_t)c0 * in_stride, out + (size_t)c0 * out_stride,
                                           s1 + (size_t)c0 * (M + 1) * N * N, s2 + (size_t)c0 * (M + 1) * 2 * N * N, backward,
@@ -525,6 +558,7 @@ static int run(const lct_plan* plan, const float* in, const int32_t* tbe, const 
     GpuLauncher l{stream, plan->device};
     l.events = events;
     l.prefetch_ahead = plan->prefetch_ahead;
+    l.pdl = plan->pdl;
     for (long long c0 = 0; c0 < C; c0 += chunk) {
         const int cn = (int)((C - c0 < chunk) ? (C - c0) : chunk);
         const int rc = lct::run_chain(l, t, M, N, cn, D, Tin, tbe[0], be_dev, (int)c0,

@@ -58,7 +58,9 @@ template <int N> struct PlaneKernel {
     using PHp = typename ColPlan<2 * N>::type;
     static constexpr int kFull = N * PHp::TL;                               // one column batch
     static constexpr int NT = kFull < kPlaneThreads ? kFull : kPlaneThreads;
-    using type = PlaneFilter<PHp, typename ColPlan<N>::type, NT>;
+    // persistent walk with the next plane staged by the bulk-copy unit: at N = 64 (measured); the smaller planes
+    // are a few KB and their kernels are launch-bound
+    using type = PlaneFilter<PHp, typename ColPlan<N>::type, NT, (LCT_PLANE_PERSIST && N == 64)>;
 };
 // H-frequency held by plane row r after the forward H stages (the fused filter is stored in this order)
 template <int N> int plane_row_freq(int r) { return ColPlan<2 * N>::type::pos_to_freq(r); }

@@ -97,7 +97,7 @@ template <int L> struct TwShared {
     static inline void fill(unsigned char*, int, int) {}
 #else
     static LCT_DEV float2 get(int i) {
-        extern __shared__ __align__(16) unsigned char lct_dyn_smem[];
+        extern __shared__ __align__(128) unsigned char lct_dyn_smem[];
         return reinterpret_cast<const float2*>(lct_dyn_smem)[i / (kTwN / L)];
     }
     static LCT_DEV void fill(unsigned char* smem, int tid, int nthreads) {
@@ -122,7 +122,7 @@ template <class P> struct TwLine {
     static inline void fill(unsigned char*, int, int) {}
 #else
     static LCT_DEV float2 at(int k, int lo) {
-        extern __shared__ __align__(16) unsigned char lct_dyn_smem[];
+        extern __shared__ __align__(128) unsigned char lct_dyn_smem[];
         return reinterpret_cast<const float2*>(lct_dyn_smem)[k * STR0 + lo];
     }
     static LCT_DEV void fill(unsigned char* smem, int tid, int nthreads) {
@@ -211,6 +211,11 @@ struct Params {
     // time kernels: how many blocks ahead (in launch order) the tile to warm in L2 lies; 0 = no prefetch.
     // The launcher sets it to the number of resident blocks, so the lines arrive about one block life early.
     int ahead;
+    // programmatic dependent launch: 0 = plain stream order, 1 = every block releases the next kernel of the stream as
+    // soon as it starts (that kernel's blocks then take the SMs the tail of this one leaves idle, run their prologue
+    // and sleep in griddepcontrol.wait until this grid has finished and flushed).  Releasing only after the last phase
+    // measured the same or slower.
+    int pdl;
 };
 
 LCT_DEV void prefetch_l2(const void* ptr) {
@@ -240,6 +245,62 @@ LCT_DEV void cp_async_commit() {
 LCT_DEV void cp_async_wait_all() {
 #ifndef LCT_EMULATE
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
+// Bulk asynchronous copy (the TMA unit's one-dimensional form, cp.async.bulk) + mbarrier: one thread asks for a whole
+// contiguous run of bytes; they land in shared memory without passing through any thread's registers or issue slots
+// and complete the barrier's transaction count.  `bulk_load` both announces the bytes on the barrier and starts the
+// copy, so every issuing thread accounts for exactly what it asked for.  Source, destination and size must be
+// multiples of 16 bytes.  The emulator copies at issue time (one legal outcome) and its barriers are no-ops.
+LCT_DEV void mbar_init(unsigned long long* bar, unsigned count) {
+#ifndef LCT_EMULATE
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#else
+    (void)bar; (void)count;
+#endif
+}
+// one arrival that also announces `bytes` of pending bulk copies (the barrier's phase completes when every expected
+// arrival has happened and every announced byte has landed)
+LCT_DEV void mbar_arrive_expect(unsigned long long* bar, unsigned bytes) {
+#ifndef LCT_EMULATE
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+#else
+    (void)bar; (void)bytes;
+#endif
+}
+LCT_DEV void bulk_load(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar) {
+#ifndef LCT_EMULATE
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+#else
+    (void)bar;
+    std::memcpy(dst_smem, src, bytes);
+#endif
+}
+LCT_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
+#ifndef LCT_EMULATE
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "LCT_MBAR_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LCT_MBAR_DONE_%=;\n\t"
+        "bra LCT_MBAR_WAIT_%=;\n\t"
+        "LCT_MBAR_DONE_%=:\n\t}" ::"r"(b), "r"(parity) : "memory");
+#else
+    (void)bar; (void)parity;
+#endif
+}
+// orders this thread's (and, after a barrier, the block's) earlier generic accesses to shared memory before later
+// accesses of the asynchronous proxy: needed before a bulk copy overwrites a buffer the threads have just used
+LCT_DEV void fence_proxy_async() {
+#ifndef LCT_EMULATE
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
 }
 
@@ -524,6 +585,11 @@ template <class P, int CT_> struct TimeFwdPersistent {
         else { gx = p.N * p.N / CT; gy = p.C; }              // one tile per block: (column tile, channel)
     }
     static int iterations(const Params& p) { return kPersist ? TileWalk(p, p.N * p.N / CT).iterations() : 1; }
+    static constexpr bool kTileWalks = true;              // see TimeInv::walk_active
+    static LCT_DEV bool walk_active(const Params& p, int bx, int, int it) {
+        const TileWalk walk(p, p.N * p.N / CT, kPersist);
+        return !kPersist || bx + it * walk.G < walk.total;
+    }
 
     static constexpr bool kHasPrologue = true;
     static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwS::fill(smem, tid, kThreads); }
@@ -559,7 +625,9 @@ template <class P, int CT_> struct TimeFwdPersistent {
         int tile, col0, c;
         if constexpr (kPersist) {
             tile = bx + it * walk.G;
-            if (tile >= walk.total) return;                  // block-uniform: the barriers are in the driver
+#ifdef LCT_EMULATE
+            if (tile >= walk.total) return;                  // on the GPU the driver leaves the loop (walk_active)
+#endif
             col0 = (tile & (tpc - 1)) * CT;
             c = tile >> ilog2_pow2(tpc);
         } else {
@@ -671,22 +739,60 @@ template <class P, int CT_> struct TimeInv {
     // tile next to it (registers cap the kernel at two blocks per SM anyway; saves a phase)
     static constexpr size_t kZs = ((size_t)(M + 1) * CT * sizeof(float2) + 15) / 16 * 16;
     static constexpr size_t kWork = kZs + (size_t)(M + 2) * CT * sizeof(float);
-    static constexpr size_t kSmem = TwS::kBytes + (kWork + (size_t)M * sizeof(float4)) + 32;  // + the operator's row records + MinMaxSlot
+    static constexpr size_t kBarRel = kWork + (size_t)M * sizeof(float4) + 32;    // behind the row records and the MinMaxSlot
+    static constexpr size_t kSmem = TwS::kBytes + kBarRel + 16;
     static constexpr bool kWarpSync = false;
     // 1024 threads/SM at <= 64 regs; the 32-wide butterflies need 128 regs (512 threads/SM)
     static constexpr int kMinBlocks = (P::E >= 32) ? (512 / kThreads > 0 ? 512 / kThreads : 1) : ((kThreads >= 1024) ? 1 : 1024 / kThreads);
     struct Regs { float2 a[P::E]; };
     static void grid(const Params& p, int& gx, int& gy) { gx = TileWalk(p, p.N * p.N / CT).G; gy = 1; }
     static int iterations(const Params& p) { return TileWalk(p, p.N * p.N / CT).iterations(); }
+#ifndef LCT_TIME_INV_DRIVER_EXIT
+#define LCT_TIME_INV_DRIVER_EXIT 0
+#endif
+    // Block-uniform: false once the block's walk has run past the last tile.  When the driver tests it (once per
+    // iteration) the phases carry no early return, the compiler sees that nothing in Regs lives from one tile to the
+    // next and the three 64-bit spills and reloads of r.a per tile disappear -- and the kernel runs 6-12 % slower
+    // (221 -> 234 us at 8 x 512x128^2, 100 -> 112 at 16 x 128^3, 37.0 -> 39.6 at 8 x 256x64^2): the reload only ever
+    // showed up in the profile because it is the first instruction behind the wait for the tile.  Off for this kernel.
+    static constexpr bool kDriverExit = LCT_TIME_INV_DRIVER_EXIT;
+    static LCT_DEV bool walk_active(const Params& p, int bx, int, int it) {
+        const TileWalk walk(p, p.N * p.N / CT);
+        return !kDriverExit || bx + it * walk.G < walk.total;
+    }
+    static constexpr bool kTileWalks = true;
 
     static constexpr bool kHasPrologue = true;
     static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) {
         TwS::fill(smem, tid, kThreads);
         if (tid == 0) minmax_slot_init(reinterpret_cast<MinMaxSlot*>(smem + TwS::kBytes + kWork + (size_t)M * sizeof(float4)));
+        if (kBulk && tid == 0) mbar_init(reinterpret_cast<unsigned long long*>(smem + TwS::kBytes + kBarRel), 1);
+    }
+
+#ifndef LCT_TIME_INV_BULK
+#define LCT_TIME_INV_BULK 0
+#endif
+    // Bulk mode: every row of the tile is CT * 8 contiguous bytes of S1, so thread t asks the bulk-copy unit for row t
+    // (one instruction where the 16-byte copies below take (M + 1) * CT / 2 / kThreads, with their addresses) and the
+    // rows complete one mbarrier; thread 0 makes the single arrival and announces the whole tile's bytes.
+    static constexpr bool kBulk = LCT_TIME_INV_BULK && (CT * sizeof(float2)) % 16 == 0;
+    static LCT_DEV void wait_tile(unsigned char* smem, int it) {
+        if constexpr (kBulk) mbar_wait(reinterpret_cast<unsigned long long*>(smem + kBarRel), (unsigned)(it & 1));
+        else cp_async_wait_all();
+    }
+    static LCT_DEV void issue_tile_bulk(const Params& p, unsigned char* smem, int tid, int tile) {
+        constexpr unsigned kRowBytes = CT * sizeof(float2);
+        const int NN = p.N * p.N, tpc = NN / CT, c = tile >> ilog2_pow2(tpc), col0 = (tile & (tpc - 1)) * CT;
+        const float2* src = p.s1 + (size_t)c * (M + 1) * NN + col0;
+        unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + kBarRel);
+        fence_proxy_async();                      // the stages' accesses to zs (ordered by the barrier) before the copies
+        if (tid == 0) mbar_arrive_expect(bar, (unsigned)(M + 1) * kRowBytes);
+        for (int k = tid; k <= M; k += kThreads) bulk_load(smem + (size_t)k * kRowBytes, src + (size_t)k * NN, kRowBytes, bar);
     }
 
     // spectrum tile -> zs[(M+1)][CT] c64 by 16-byte asynchronous copies (two columns each)
     static LCT_DEV void issue_tile(const Params& p, unsigned char* smem, int tid, int tile) {
+        if constexpr (kBulk) { issue_tile_bulk(p, smem, tid, tile); return; }
         constexpr int V2 = CT / 2, kSlots = (M + 1) * V2;
         static_assert(kThreads % V2 == 0, "column pair must be fixed per thread");
         constexpr int kIters = (kSlots + kThreads - 1) / kThreads;
@@ -707,6 +813,9 @@ template <class P, int CT_> struct TimeInv {
         const int NN = p.N * p.N, tpc = NN / CT;
         const TileWalk walk(p, tpc);
         const int tile = bx + it * walk.G;
+#ifndef LCT_EMULATE
+        if constexpr (!kDriverExit)
+#endif
         if (tile >= walk.total) return;                      // block-uniform: the barriers are in the driver
         const int col0 = (tile & (tpc - 1)) * CT, c = tile >> ilog2_pow2(tpc);
         float2* zs = reinterpret_cast<float2*>(smem);
@@ -717,7 +826,7 @@ template <class P, int CT_> struct TimeInv {
                 for (int j = tid; j < M; j += kThreads) reinterpret_cast<float4*>(smem + kWork)[j] = LCT_LDG(p.ell + j);
                 issue_tile(p, smem, tid, tile);
             }
-            cp_async_wait_all();                             // later tiles were issued during the previous tile's gather
+            wait_tile(smem, it);                             // later tiles were issued during the previous tile's gather
         } else if constexpr (PH == 1) {
             // Z[k] = (X[k] + conj X[M-k]) + i conj(w^k) (X[k] - conj X[M-k])
             auto z_at = [&](int k) -> float2 {
@@ -1309,7 +1418,15 @@ template <class P, int RB_, bool SYM = false> struct ColFilterSplit {
 //                warp-uniform and the filter, stored as [kt][kw/2][row][kw&1], is read coalesced.
 //   H inverse  : K4's stages, written back over the input plane in S1.
 // ---------------------------------------------------------------------------
-template <class PHp, class PWp, int NT_> struct PlaneFilter {
+//
+// PERSIST (N = 64): about as many blocks as are resident together walk the planes (channel fastest, so the blocks
+// that are resident together share a filter plane), and while a block runs the two H-inverse phases of one plane, the bulk-copy
+// unit brings the next plane -- 8 N^2 contiguous bytes of S1 -- into the side buffer X, which the W pass has just
+// released; the first H stage then reads its inputs from shared memory instead of waiting for L2.
+#ifndef LCT_PLANE_PERSIST
+#define LCT_PLANE_PERSIST 0
+#endif
+template <class PHp, class PWp, int NT_, bool PERSIST = false> struct PlaneFilter {
     static constexpr int L = PHp::L, N = L / 2;
     static_assert(PWp::L == N && PWp::S == 2 && PHp::S == 2, "plane fusion needs two-stage plans");
     static constexpr int kThreads = NT_;
@@ -1324,18 +1441,47 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
     static constexpr size_t kTwBytes = TwP::kBytes;
     // plane T[L][RS] + side buffer X[RBt][RS]: the odd-parity transform of a row batch is exchanged
     // through X while the even one uses the rows' own slots, so both run in the same three phases
-    static constexpr size_t kSmem = kTwBytes + (size_t)(L + RBt) * RS * sizeof(float2);
+    static constexpr size_t kPlaneBytes = (size_t)N * N * sizeof(float2);
+    static_assert(!PERSIST || (size_t)RBt * RS * sizeof(float2) >= kPlaneBytes, "the next plane is staged in X");
+    static_assert(!PERSIST || (kTwBytes + (size_t)L * RS * sizeof(float2)) % 16 == 0, "bulk copies land on 16-byte boundaries");
+    static constexpr size_t kBarOff = kTwBytes + (size_t)(L + RBt) * RS * sizeof(float2);
+    static constexpr size_t kSmem = kBarOff + (PERSIST ? 16 : 0);
     static constexpr int kPhases = 2 + nWB * 3 + 2;
     static constexpr int EW = PWp::E;
     static constexpr bool kWarpSync = false;
     static constexpr int kMinBlocks = (2 * kSmem <= 220 * 1024) ? 2 : 1;      // two blocks per SM at <= 64 registers
     struct Regs {};
-    static void grid(const Params& p, int& gx, int& gy) { gx = p.C; gy = p.M + 1; }   // c fastest: filter plane reused from L2
-    static int iterations(const Params&) { return 1; }
+    // PERSIST: grid (C, R) with R = resident blocks / C rows of planes; block (c, r) walks kt = r, r + R, ... -- a
+    // two-dimensional grid keeps the plane index free of divisions and in the uniform datapath (a flat walk that
+    // split its index by C in every phase cost the kernel 7 % more instructions than the prefetch saved)
+    static LCT_HD int walk_rows(const Params& p) {
+        const int r = (PERSIST && p.ahead > 0) ? p.ahead / p.C : p.M + 1;
+        return r < 1 ? 1 : (r > p.M + 1 ? p.M + 1 : r);
+    }
+    static void grid(const Params& p, int& gx, int& gy) { gx = p.C; gy = walk_rows(p); }   // c fastest: filter plane reused from L2
+    static int iterations(const Params& p) { return (p.M + 1 + walk_rows(p) - 1) / walk_rows(p); }
+    static LCT_DEV int rows_of_grid(const Params& p) {
+#ifdef LCT_EMULATE
+        return walk_rows(p);
+#else
+        return (int)gridDim.y;
+#endif
+    }
+    static constexpr bool kTileWalks = true;              // see TimeInv::walk_active
+    static LCT_DEV bool walk_active(const Params& p, int, int by, int it) { return !PERSIST || by + it * rows_of_grid(p) <= p.M; }
 
     static constexpr bool kHasPrologue = true;
     static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) {
         TwP::fill(smem, tid, kThreads);
+        if (PERSIST && tid == 0) mbar_init(reinterpret_cast<unsigned long long*>(smem + kBarOff), 1);
+    }
+    // plane (c, kt) -> X, as N x N dense c64; one thread asks, the barrier collects
+    static LCT_DEV void stage_plane(const Params& p, unsigned char* smem, int c, int kt) {
+        unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + kBarOff);
+        fence_proxy_async();
+        mbar_arrive_expect(bar, (unsigned)kPlaneBytes);
+        bulk_load(smem + kTwBytes + (size_t)L * RS * sizeof(float2), p.s1 + ((size_t)c * (p.M + 1) + kt) * N * N,
+                  (unsigned)kPlaneBytes, bar);
     }
 #ifndef LCT_PLANE_GROUPSYNC
 #define LCT_PLANE_GROUPSYNC 2
@@ -1354,19 +1500,34 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
         return (kGroupSync && ph >= 2 && ph < 2 + 3 * nWB - 1) || (kGroupSyncH && (ph == 0 || ph == 2 + 3 * nWB));
     }
 
-    template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem, int tid, int bx, int by, int) {
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem, int tid, int bx, int by, int it) {
         float2* T = reinterpret_cast<float2*>(smem + kTwBytes);
         float2* X = T + L * RS;
-        const int kt = by;
+        const int rows = PERSIST ? rows_of_grid(p) : 0, kt = by + it * rows;
+#ifdef LCT_EMULATE
+        if (kt > p.M) return;                                // on the GPU the driver leaves the loop (walk_active)
+#endif
         const size_t plane = (size_t)bx * (p.M + 1) + kt;
         constexpr int kW0 = 2, kW1 = 2 + 3 * nWB;
+        if constexpr (PH == 0 && PERSIST) {
+#ifdef LCT_EMULATE
+            if (it == 0) stage_plane(p, smem, bx, kt);       // every emulated thread copies before it reads (any thread order)
+#else
+            if (it == 0 && tid == 0) stage_plane(p, smem, bx, kt);        // later planes were asked for during the H inverse
+#endif
+            mbar_wait(reinterpret_cast<unsigned long long*>(smem + kBarOff), (unsigned)(it & 1));
+        }
+        if constexpr (PH == kW1 && PERSIST) {
+            // the W pass is over (whole-block barrier): X is free until the next plane's W pass
+            if (tid == 0 && kt + rows <= p.M) stage_plane(p, smem, bx, kt + rows);
+        }
         if constexpr (PH < kW0) {
             // H forward; column batches touch disjoint columns, so they share a phase
             const int tau = line_thread<CB>(tid);
             LCT_UNROLL
             for (int hb = 0; hb < nHB; ++hb) {
                 const int col = hb * CB + tid % CB;
-                const float2* src = p.s1 + plane * N * N + col;
+                const float2* src = PERSIST ? X + col : p.s1 + plane * N * N + col;
                 if constexpr (PH == 0) {
                     fwd_stage<PHp, 0, true, TwP>(tau,
                         [&](int pos, int) { return src[(size_t)pos * N]; },
@@ -1480,6 +1641,9 @@ template <class PHp, class PWp, int NT_> struct PlaneFilter {
 template <class K, class = void> struct has_prologue { static constexpr bool value = false; };
 template <class K> struct has_prologue<K, decltype((void)K::kHasPrologue)> { static constexpr bool value = true; };
 
+template <class K, class = void> struct has_tile_walk { static constexpr bool value = false; };
+template <class K> struct has_tile_walk<K, decltype((void)K::kTileWalks)> { static constexpr bool value = true; };
+
 template <class K, class = void> struct has_group_sync { static constexpr bool value = false; };
 template <class K> struct has_group_sync<K, decltype((void)K::kGroupSync)> { static constexpr bool value = true; };
 
@@ -1499,14 +1663,20 @@ template <class K, int PH> struct PhaseLoop {
     }
 };
 
-template <class K> __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) lct_kernel(const Params p, const int iters) {
-    extern __shared__ __align__(16) unsigned char smem[];
+template <class K> __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) lct_kernel(const __grid_constant__ Params p, const int iters) {
+    extern __shared__ __align__(128) unsigned char smem[];
     typename K::Regs r;
-    if constexpr (has_prologue<K>::value) {
-        K::prologue(p, r, smem, threadIdx.x, blockIdx.x, blockIdx.y);
-        __syncthreads();
+    // the prologue only touches plan constants (twiddle and operator tables) and shared memory: it may run while the
+    // previous kernel of the stream is still draining
+    if constexpr (has_prologue<K>::value) K::prologue(p, r, smem, threadIdx.x, blockIdx.x, blockIdx.y);
+    asm volatile("griddepcontrol.wait;" ::: "memory");                   // no-op for a plain launch
+    if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if constexpr (has_prologue<K>::value) __syncthreads();
+    for (int it = 0; it < iters; ++it) {
+        if constexpr (has_tile_walk<K>::value)
+            if (!K::walk_active(p, blockIdx.x, blockIdx.y, it)) break;
+        PhaseLoop<K, 0>::run(p, r, smem, it);
     }
-    for (int it = 0; it < iters; ++it) PhaseLoop<K, 0>::run(p, r, smem, it);
 }
 #endif
 
