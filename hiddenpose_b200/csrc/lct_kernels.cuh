@@ -1172,7 +1172,10 @@ template <class P, int RB_, bool SYM = false> struct ColFilter {
     // all threads of a line sit in one warp (tid % TL), so the exchanges only need __syncwarp:
     // warps run through the channel loop independently of each other.
     static constexpr bool kWarpSync = true;
-    static constexpr int kMinBlocks = (P::E <= 16) ? 2 : 1;
+#ifndef LCT_COLFILTER_BLOCKS
+#define LCT_COLFILTER_BLOCKS 2
+#endif
+    static constexpr int kMinBlocks = (P::E <= 16) ? LCT_COLFILTER_BLOCKS : 1;
     static constexpr int PAD = 1;
     static constexpr int RS = L + P::R0 * PAD + ((P::TL < 16) ? 8 : 0);    // row stride in float2
     static constexpr size_t kSmem = TwL::kBytes + (size_t)RB * RS * sizeof(float2);
