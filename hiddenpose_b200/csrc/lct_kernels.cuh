@@ -868,13 +868,21 @@ template <class P, int CT_> struct TimeInv {
             const size_t step = (size_t)P::TL * NN;
             const float* vc = vol + col;
             const float4* ell = reinterpret_cast<const float4*>(smem + kWork);
+#ifndef LCT_TIME_INV_TRIP_COUNT
+#define LCT_TIME_INV_TRIP_COUNT 1
+#endif
+            // outputs tau, tau + TL, ... below out_T: a warp-uniform trip count instead of a test per output -- the
+            // uniform branch around every output kept the compiler from batching the loads of one unrolled group,
+            // so each output waited out its own shared-memory round trip (wait + short_scoreboard were 53 % of this
+            // phase's stall samples, and the phase is 39 % of the kernel)
+            const int rows_out = LCT_TIME_INV_TRIP_COUNT ? (p.out_T - tau + P::TL - 1) / P::TL : M / P::TL;
             if (p.minmax_keys == nullptr) {
                 [[maybe_unused]] const float4* er = ell + be + tau;         // mtxi rows have at most three entries: no tail
 #ifndef LCT_EMULATE
 #pragma unroll 8                                   // full unrolling (16) measured 2 % slower at M = 256
 #endif
-                for (int m = 0; m < M / P::TL; ++m, d += step)
-                    if (tau + m * P::TL < p.out_T) {
+                for (int m = 0; m < rows_out; ++m, d += step)
+                    if (LCT_TIME_INV_TRIP_COUNT || tau + m * P::TL < p.out_T) {
                         if constexpr (LCT_MTXI_CLOSED_FORM) *d = band_dot_sq<CT, P::ilog2(M)>(ell, be + tau + m * P::TL, vc);
                         else *d = band_dot<false, CT>(p, er, m * P::TL, vc);
                     }
@@ -891,8 +899,8 @@ template <class P, int CT_> struct TimeInv {
 #ifndef LCT_EMULATE
 #pragma unroll 8
 #endif
-                for (int m = 0; m < M / P::TL; ++m, d += step)
-                    if (tau + m * P::TL < p.out_T) {
+                for (int m = 0; m < rows_out; ++m, d += step)
+                    if (LCT_TIME_INV_TRIP_COUNT || tau + m * P::TL < p.out_T) {
                         float v;
                         if constexpr (LCT_MTXI_CLOSED_FORM) v = band_dot_sq<CT, P::ilog2(M)>(ell, be + tau + m * P::TL, vc);
                         else v = band_dot<false, CT>(p, er, m * P::TL, vc);

@@ -358,6 +358,31 @@ def test_two_threads_share_one_plan_on_two_streams():
     assert not errors, errors
 
 
+@pytest.mark.parametrize("N,M,B", [(64, 64, 6), (128, 32, 3)])
+def test_dependent_launch_keeps_stream_order(monkeypatch, N, M, B):
+    """The kernels of a chain are launched programmatically dependent (LCT_PDL, default on): each may start while its
+    predecessor drains and orders itself with griddepcontrol.wait.  Back-to-back calls that reuse one workspace (the
+    next call's first kernel overwrites the spectrum the previous call's last kernel reads), forward and backward
+    mixed, must give the bits of a plan that launches in plain stream order."""
+    monkeypatch.setenv("LCT_PDL", "0")
+    plain = _layer(N, M, 0.04, 1)
+    monkeypatch.setenv("LCT_PDL", "1")
+    pdl = _layer(N, M, 0.04, 1)
+    xs = [torch.rand(B, 1, M, N, N, device="cuda") for _ in range(4)]
+    gs = [torch.randn(B, 1, M, N, N, device="cuda") for _ in range(4)]
+    tb, te = [0] * B, [M] * B
+    with torch.no_grad():
+        want = [(plain(x, tb, te).clone(), plain._plan.backward(g, tb, te, M).clone()) for x, g in zip(xs, gs)]
+        torch.cuda.synchronize()
+        for _ in range(5):
+            got = []
+            for x, g in zip(xs, gs):          # no synchronisation between the calls; torch's caching allocator hands
+                got.append((pdl._plan.forward(x, tb, te), pdl._plan.backward(g, tb, te, M)))   # every call the same workspace block
+            torch.cuda.synchronize()
+            for (y, gx), (wy, wgx) in zip(got, want):
+                assert torch.equal(y, wy) and torch.equal(gx, wgx)
+
+
 def test_numpy_path_of_the_reference(parity_log):
     """the CUDA volume against the outputs of /root/reference/utils/lct.py itself
     (tests/golden/make_golden_numpy_lct.py): the un-clamped volume (lct.py:41-59) and the three displayed views."""
