@@ -9,7 +9,7 @@ from hiddenpose_b200 import operators as ops
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SO = os.path.join(HERE, "liblct_emu.so")
+SO = os.environ.get("LCT_EMU_SO") or os.path.join(HERE, "liblct_emu.so")      # override + LCT_EMU_DEFS: variant builds
 CSRC = os.path.join(ROOT, "hiddenpose_b200", "csrc")
 
 

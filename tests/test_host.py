@@ -207,6 +207,40 @@ def test_emulated_set_barriers_tolerate_maximal_drift(N):
         assert np.array_equal(base, plan.run(x, 1, M, [0, 0], drift=drift, reverse=True)[0])
 
 
+def test_emulated_measured_and_rejected_variants_still_compute_the_same():
+    """The kernel variants that were measured and left off (persistent plane kernel with the next plane
+    staged by a bulk copy, K5's tile through per-row bulk copies, K5's tile-walk exit test in the kernel driver) stay
+    compilable and correct: a second emulator build with them switched on, in a subprocess, must reproduce the default
+    build bit for bit (any thread order, maximal set drift)."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = (
+        "import sys, numpy as np\n"
+        "from tests.emu.emu import EmuPlan\n"
+        "out = {}\n"
+        "for N, M, C in ((64, 32, 3), (16, 64, 2)):\n"
+        "    plan = EmuPlan(N, M, 0.16)\n"
+        "    x = np.random.RandomState(N).rand(C, M - 3, N, N).astype(np.float32)\n"
+        "    y = plan.run(x, 1, M - 3, [2] * C)[0]\n"
+        "    assert np.array_equal(y, plan.run(x, 1, M - 3, [2] * C, reverse=True)[0])\n"
+        "    if N == 64:\n"
+        "        assert np.array_equal(y, plan.run(x, 1, M - 3, [2] * C, drift=1)[0])\n"
+        "    out['y%d' % N] = y\n"
+        "np.savez(sys.argv[1], **out)\n")
+    results = []
+    for tag, defs in (("default", ""), ("variants", "-DLCT_PLANE_PERSIST=1 -DLCT_TIME_INV_BULK=1 -DLCT_TIME_INV_DRIVER_EXIT=1")):
+        env = dict(os.environ, LCT_EMU_DEFS=defs)
+        if defs:
+            env["LCT_EMU_SO"] = os.path.join(here, "emu", "liblct_emu_variants.so")
+        path = os.path.join(here, "emu", f"_variant_check_{tag}.npz")
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, cwd=os.path.dirname(here))
+        results.append(dict(np.load(path)))
+        os.remove(path)
+    for k in results[0]:
+        assert np.array_equal(results[0][k], results[1][k]), k
+
+
 def test_operator_structure_is_validated():
     """The kernels look for rows longer than three taps only among the first few rows of mtx and never in
     mtx^T (lct_tables.h); an operator that breaks this must be refused, not silently truncated."""
