@@ -457,6 +457,8 @@ template <class P, int CT_> struct TimeFwd {
     struct Regs {};
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N * p.N / CT; gy = p.C; }
     static int iterations(const Params&) { return 1; }
+    // One pass per block, but the loop stays: without it (kSinglePass) this kernel compiles to fewer registers and runs
+    // slower (M = 128: 98 vs 90 us at 16 x 128^3; M = 256: no change).
 
     static constexpr bool kHasPrologue = true;
     static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwS::fill(smem, tid, kThreads); }
@@ -943,6 +945,7 @@ template <class P, int CT_> struct RowFwd {
     struct Regs {};
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N / CT; gy = p.C * (p.M + 1); }
     static int iterations(const Params&) { return 1; }
+    static constexpr bool kSinglePass = true;       // the driver runs the phases once, without a loop (K2 295 -> 293 us at 8 x 512x128^2)
 
     static constexpr bool kHasPrologue = true;
     static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwS::fill(smem, tid, kThreads); }
@@ -995,6 +998,7 @@ template <class P, int CT_> struct RowInv {
     struct Regs {};
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N / CT; gy = p.C * (p.M + 1); }
     static int iterations(const Params&) { return 1; }
+    static constexpr bool kSinglePass = true;       // the driver runs the phases once, without a loop: K4 273 -> 252 us at 8 x 512x128^2, 146 -> 135 at 16 x 128^3
 
     static constexpr bool kHasPrologue = true;
     static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwS::fill(smem, tid, kThreads); }
@@ -1056,6 +1060,7 @@ template <class P, int CT_> struct RowFwdSplit {
     struct Regs {};
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N / CT; gy = p.C * (p.M + 1); }
     static int iterations(const Params&) { return 1; }
+    static constexpr bool kSinglePass = false;      // (single pass measured slower here: 188 vs 178 us at 512x256^2)
 
     static constexpr bool kHasPrologue = true;
     static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwS::fill(smem, tid, kThreads); }
@@ -1108,6 +1113,7 @@ template <class P, int CT_> struct RowInvSplit {
     struct Regs {};
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N / CT; gy = p.C * (p.M + 1); }
     static int iterations(const Params&) { return 1; }
+    static constexpr bool kSinglePass = false;      // (single pass: no difference)
 
     static constexpr bool kHasPrologue = true;
     static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwS::fill(smem, tid, kThreads); }
@@ -1170,6 +1176,8 @@ template <int N> LCT_DEV int sym_twist(int k) { return k <= N ? 0 : k; }
 // plane; it loops over the channels so the filter row stays in registers.
 // Two-stage plans only (lanes run along the line so global accesses coalesce).
 // ---------------------------------------------------------------------------
+// (An instantiation without the channel loop for single-channel launches, as the H-axis kernels have it, measured slower:
+//  416 vs 408 us at 512x256^2, 123 vs 119 us at 1 x 512x128^2.)
 template <class P, int RB_, bool SYM = false> struct ColFilter {
     static_assert(P::S == 2, "ColFilter needs a two-stage plan");
     static_assert(32 % P::TL == 0, "the threads of one line must share a warp");
@@ -1461,7 +1469,19 @@ template <class PHp, class PWp, int NT_, bool PERSIST = false> struct PlaneFilte
     static constexpr int EW = PWp::E;
     static constexpr bool kWarpSync = false;
     static constexpr int kMinBlocks = (2 * kSmem <= 220 * 1024) ? 2 : 1;      // two blocks per SM at <= 64 registers
-    struct Regs {};
+#ifndef LCT_PLANE_PRELOAD
+#define LCT_PLANE_PRELOAD 1
+#endif
+    // The first H stage's inputs are requested before the barrier that ends the prologue (the twiddle-table fill), so
+    // the plane's L2 round trip and the table's overlap instead of following each other at the start of every block.
+    static constexpr bool kPreload = LCT_PLANE_PRELOAD && !PERSIST && nHB == 1;
+    struct Regs { float2 in[kPreload ? PHp::E : 1]; };
+    static LCT_DEV void preload(const Params& p, Regs& r, unsigned char*, int tid, int bx, int by) {
+        if constexpr (kPreload) {
+            const float2* src = p.s1 + ((size_t)bx * (p.M + 1) + by) * N * N + tid % CB;
+            for_each_slot_lower<PHp, 0>(line_thread<CB>(tid), [&](int pos, int slot) { r.in[slot] = src[(size_t)pos * N]; });
+        }
+    }
     // PERSIST: grid (C, R) with R = resident blocks / C rows of planes; block (c, r) walks kt = r, r + R, ... -- a
     // two-dimensional grid keeps the plane index free of divisions and in the uniform datapath (a flat walk that
     // split its index by C in every phase cost the kernel 7 % more instructions than the prefetch saved)
@@ -1479,6 +1499,7 @@ template <class PHp, class PWp, int NT_, bool PERSIST = false> struct PlaneFilte
 #endif
     }
     static constexpr bool kTileWalks = true;              // see TimeInv::walk_active
+    static constexpr bool kSinglePass = !PERSIST;         // iterations() == 1: the driver runs the phases without a loop
     static LCT_DEV bool walk_active(const Params& p, int, int by, int it) { return !PERSIST || by + it * rows_of_grid(p) <= p.M; }
 
     static constexpr bool kHasPrologue = true;
@@ -1511,7 +1532,7 @@ template <class PHp, class PWp, int NT_, bool PERSIST = false> struct PlaneFilte
         return (kGroupSync && ph >= 2 && ph < 2 + 3 * nWB - 1) || (kGroupSyncH && (ph == 0 || ph == 2 + 3 * nWB));
     }
 
-    template <int PH> static LCT_DEV void phase(const Params& p, Regs&, unsigned char* smem, int tid, int bx, int by, int it) {
+    template <int PH> static LCT_DEV void phase(const Params& p, Regs& r, unsigned char* smem, int tid, int bx, int by, int it) {
         float2* T = reinterpret_cast<float2*>(smem + kTwBytes);
         float2* X = T + L * RS;
         const int rows = PERSIST ? rows_of_grid(p) : 0, kt = by + it * rows;
@@ -1539,7 +1560,11 @@ template <class PHp, class PWp, int NT_, bool PERSIST = false> struct PlaneFilte
             for (int hb = 0; hb < nHB; ++hb) {
                 const int col = hb * CB + tid % CB;
                 const float2* src = PERSIST ? X + col : p.s1 + plane * N * N + col;
-                if constexpr (PH == 0) {
+                if constexpr (PH == 0 && kPreload) {
+                    fwd_stage<PHp, 0, true, TwP>(tau,
+                        [&](int, int slot) { return r.in[slot]; },
+                        [&](int pos, int, float2 v) { T[pos * RS + col] = v; });
+                } else if constexpr (PH == 0) {
                     fwd_stage<PHp, 0, true, TwP>(tau,
                         [&](int pos, int) { return src[(size_t)pos * N]; },
                         [&](int pos, int, float2 v) { T[pos * RS + col] = v; });
@@ -1652,6 +1677,12 @@ template <class PHp, class PWp, int NT_, bool PERSIST = false> struct PlaneFilte
 template <class K, class = void> struct has_prologue { static constexpr bool value = false; };
 template <class K> struct has_prologue<K, decltype((void)K::kHasPrologue)> { static constexpr bool value = true; };
 
+template <class K, class = void> struct has_preload { static constexpr bool value = false; };
+template <class K> struct has_preload<K, decltype((void)K::kPreload)> { static constexpr bool value = true; };
+
+template <class K, class = void> struct has_single_pass { static constexpr bool value = false; };
+template <class K> struct has_single_pass<K, std::enable_if_t<K::kSinglePass>> { static constexpr bool value = true; };
+
 template <class K, class = void> struct has_tile_walk { static constexpr bool value = false; };
 template <class K> struct has_tile_walk<K, decltype((void)K::kTileWalks)> { static constexpr bool value = true; };
 
@@ -1682,11 +1713,16 @@ template <class K> __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks)
     if constexpr (has_prologue<K>::value) K::prologue(p, r, smem, threadIdx.x, blockIdx.x, blockIdx.y);
     asm volatile("griddepcontrol.wait;" ::: "memory");                   // no-op for a plain launch
     if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if constexpr (has_preload<K>::value) K::preload(p, r, smem, threadIdx.x, blockIdx.x, blockIdx.y);    // loads fly across the barrier
     if constexpr (has_prologue<K>::value) __syncthreads();
-    for (int it = 0; it < iters; ++it) {
-        if constexpr (has_tile_walk<K>::value)
-            if (!K::walk_active(p, blockIdx.x, blockIdx.y, it)) break;
-        PhaseLoop<K, 0>::run(p, r, smem, it);
+    if constexpr (has_single_pass<K>::value) {
+        PhaseLoop<K, 0>::run(p, r, smem, 0);                 // no loop: nothing in Regs outlives its last use
+    } else {
+        for (int it = 0; it < iters; ++it) {
+            if constexpr (has_tile_walk<K>::value)
+                if (!K::walk_active(p, blockIdx.x, blockIdx.y, it)) break;
+            PhaseLoop<K, 0>::run(p, r, smem, it);
+        }
     }
 }
 #endif

@@ -91,6 +91,8 @@ struct EmuLauncher {
                     else
                         for (int tid = K::kThreads - 1; tid >= 0; --tid) K::prologue(p, regs[tid], smem.data(), tid, bx, by);
                 }
+                if constexpr (lct::has_preload<K>::value)
+                    for (int tid = 0; tid < K::kThreads; ++tid) K::preload(p, regs[tid], smem.data(), tid, bx, by);
                 std::memset(smem.data() + K::kSmem, 0xA5, 64);
                 for (int it = 0; it < iters; ++it) {
                     if (g_drift && lct::has_group_sync<K>::value) run_phases_drifting<K>(p, regs, smem.data(), bx, by, it);
