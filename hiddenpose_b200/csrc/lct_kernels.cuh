@@ -870,6 +870,10 @@ template <class P, int CT_> struct TimeInv {
             const size_t step = (size_t)P::TL * NN;
             const float* vc = vol + col;
             const float4* ell = reinterpret_cast<const float4*>(smem + kWork);
+#ifndef LCT_K5_UNROLL
+#define LCT_K5_UNROLL 8
+#endif
+            [[maybe_unused]] constexpr int kGatherUnroll = LCT_K5_UNROLL;
 #ifndef LCT_TIME_INV_TRIP_COUNT
 #define LCT_TIME_INV_TRIP_COUNT 1
 #endif
@@ -881,7 +885,7 @@ template <class P, int CT_> struct TimeInv {
             if (p.minmax_keys == nullptr) {
                 [[maybe_unused]] const float4* er = ell + be + tau;         // mtxi rows have at most three entries: no tail
 #ifndef LCT_EMULATE
-#pragma unroll 8                                   // full unrolling (16) measured 2 % slower at M = 256
+#pragma unroll kGatherUnroll                        // 8: full unrolling (16) measured 2 % slower at M = 256
 #endif
                 for (int m = 0; m < rows_out; ++m, d += step)
                     if (LCT_TIME_INV_TRIP_COUNT || tau + m * P::TL < p.out_T) {
@@ -899,7 +903,7 @@ template <class P, int CT_> struct TimeInv {
                 float mn = kInfinity, mx = -kInfinity, poison = 0.f;
                 [[maybe_unused]] const float4* er = ell + be + tau;         // same loop shape as the plain path above
 #ifndef LCT_EMULATE
-#pragma unroll 8
+#pragma unroll kGatherUnroll
 #endif
                 for (int m = 0; m < rows_out; ++m, d += step)
                     if (LCT_TIME_INV_TRIP_COUNT || tau + m * P::TL < p.out_T) {
