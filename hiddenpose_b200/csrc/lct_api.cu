@@ -644,14 +644,46 @@ int lct_bp_laplacian(const lct_plan* plan, const float* vol, float* out, int32_t
     if (!guard.ok) return fail(LCT_ERR_CUDA, "cudaSetDevice failed");
     lct::StencilWeights w;
     std::memcpy(w.w, lapw, sizeof(float) * 125);
-    const size_t total = (size_t)channels * plan->M * plan->N * plan->N;
+    const int M = plan->M, N = plan->N;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t total = (size_t)channels * M * N * N;
     const int threads = 256;
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-    if (adjoint)
-        lct::laplacian_adjoint_kernel<<<blocks, threads, 0, (cudaStream_t)stream_>>>(vol, out, channels, plan->M, plan->N, w);
-    else
-        lct::laplacian_kernel<<<blocks, threads, 0, (cudaStream_t)stream_>>>(vol, out, channels, plan->M, plan->N, w);
+    static const bool gather_only = [] { const char* e = std::getenv("LCT_BP_GATHER"); return e && std::atoi(e) != 0; }();
+    if (gather_only || N % 4 != 0 || channels > 65535) {          // the plain gather kernels (measurement aid; any shape)
+        if (adjoint) lct::laplacian_adjoint_kernel<<<blocks, threads, 0, stream>>>(vol, out, channels, M, N, w);
+        else lct::laplacian_kernel<<<blocks, threads, 0, stream>>>(vol, out, channels, M, N, w);
+        LCT_CUDA(cudaGetLastError());
+        return LCT_OK;
+    }
+    lct::LapTiledParams p{};
+    p.in = vol; p.out = out; p.M = M; p.N = N;
+    p.rows = N < 16 ? N : 16;
+    while (p.rows * N / 4 > 512) p.rows /= 2;
+    // enough blocks for about four waves of one block per SM and warp set, but at least 16 planes per block: a block
+    // reads four planes more than it writes
+    const long long per_plane = (long long)(N / p.rows) * channels;
+    long long nchunks = (592 + per_plane - 1) / per_plane;
+    if (nchunks > M / 16) nchunks = M / 16;
+    if (nchunks < 1) nchunks = 1;
+    p.chunk = (int)((M + nchunks - 1) / nchunks);
+    p.zero_pad = adjoint ? 1 : 0;
+    if (adjoint) for (int k = 0; k < 125; ++k) p.w.w[k] = w.w[124 - k];       // taps flipped in all three axes
+    else p.w = w;
+    const dim3 grid(N / p.rows, (M + p.chunk - 1) / p.chunk, channels);
+    const int nthreads = p.rows * N / 4, slots = (p.rows + 2 * lct::kLapHalo) * (N + 2 * lct::kLapHalo);
+    const int ke = (slots + nthreads - 1) / nthreads;
+    const size_t smem = lct::lap_smem_bytes(N, p.rows);
+    if (ke <= 6) lct::laplacian_tiled_kernel<6><<<grid, nthreads, smem, stream>>>(p);
+    else if (ke <= 7) lct::laplacian_tiled_kernel<7><<<grid, nthreads, smem, stream>>>(p);
+    else if (ke <= 10) lct::laplacian_tiled_kernel<10><<<grid, nthreads, smem, stream>>>(p);
+    else return fail(LCT_ERR_UNSUPPORTED, "laplacian tile shape");
     LCT_CUDA(cudaGetLastError());
+    if (adjoint) {                                                 // the boundary shell, where clamped taps fold onto a voxel
+        const long long shell = (2LL * N * N + 2LL * (M - 2) * N + 2LL * (M - 2) * (N - 2)) * channels;
+        lct::laplacian_adjoint_shell_kernel<<<(unsigned)((shell + threads - 1) / threads), threads, 0, stream>>>(vol, out, channels, M, N, w);
+        LCT_CUDA(cudaGetLastError());
+    }
     return LCT_OK;
 }
 

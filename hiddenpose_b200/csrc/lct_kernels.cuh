@@ -34,6 +34,13 @@
 #include "lct_fft.cuh"
 #include "lct_tables.h"
 
+#ifndef LCT_K1_BLOCKS_256
+#define LCT_K1_BLOCKS_256 4      // blocks per SM the 256-thread time kernels (M = 128) are compiled for (4: 64 registers)
+#endif
+#ifndef LCT_K5_BLOCKS_256
+#define LCT_K5_BLOCKS_256 4
+#endif
+
 namespace lct {
 
 #ifdef LCT_EMULATE
@@ -453,7 +460,7 @@ template <class P, int CT_> struct TimeFwd {
     static constexpr size_t kSmem = TwS::kBytes + (kWork + (size_t)(M + kLongRows) * sizeof(float4));
     static constexpr bool kWarpSync = false;
     // 1024 threads/SM at <= 64 regs; the 32-wide butterflies need 128 regs (512 threads/SM)
-    static constexpr int kMinBlocks = (P::E >= 32) ? (512 / kThreads > 0 ? 512 / kThreads : 1) : ((kThreads >= 1024) ? 1 : 1024 / kThreads);
+    static constexpr int kMinBlocks = (P::E >= 32) ? (512 / kThreads > 0 ? 512 / kThreads : 1) : ((kThreads >= 1024) ? 1 : (kThreads == 256 ? LCT_K1_BLOCKS_256 : 1024 / kThreads));
     struct Regs {};
     static void grid(const Params& p, int& gx, int& gy) { gx = p.N * p.N / CT; gy = p.C; }
     static int iterations(const Params&) { return 1; }
@@ -745,7 +752,7 @@ template <class P, int CT_> struct TimeInv {
     static constexpr size_t kSmem = TwS::kBytes + kBarRel + 16;
     static constexpr bool kWarpSync = false;
     // 1024 threads/SM at <= 64 regs; the 32-wide butterflies need 128 regs (512 threads/SM)
-    static constexpr int kMinBlocks = (P::E >= 32) ? (512 / kThreads > 0 ? 512 / kThreads : 1) : ((kThreads >= 1024) ? 1 : 1024 / kThreads);
+    static constexpr int kMinBlocks = (P::E >= 32) ? (512 / kThreads > 0 ? 512 / kThreads : 1) : ((kThreads >= 1024) ? 1 : (kThreads == 256 ? LCT_K5_BLOCKS_256 : 1024 / kThreads));
     struct Regs { float2 a[P::E]; };
     static void grid(const Params& p, int& gx, int& gy) { gx = TileWalk(p, p.N * p.N / CT).G; gy = 1; }
     static int iterations(const Params& p) { return TileWalk(p, p.N * p.N / CT).iterations(); }

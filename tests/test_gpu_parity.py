@@ -499,6 +499,26 @@ def test_lct_graph_replays_layer_and_normalize():
         g_plain(torch.rand(2, 1, M - 4, N, N, device="cuda"))
 
 
+@pytest.mark.parametrize("M,N,C", [(32, 8, 3), (32, 16, 5), (64, 64, 2), (32, 128, 2), (32, 256, 1)])
+def test_bp_laplacian_tail_and_its_transpose(M, N, C):
+    """method == 'bp' (tflct.py:164-175): ReplicationPad3d(2) -> conv3d with the 5x5x5 filter -> zero time slice 0.
+    The tiled stencil kernel against torch's own pad + conv3d, and its transpose (tiled interior + boundary shell)
+    against autograd of that expression; every tile shape the layer can be built with."""
+    layer = _layer(N, M, 0.04, 1, method="bp")
+    plan = layer._plan
+    w = torch.from_numpy(np.asarray(plan.lapw, np.float32).reshape(1, 1, 5, 5, 5)).cuda()
+    vol = torch.randn(C, 1, M, N, N, device="cuda", requires_grad=True)
+    ref = torch.nn.functional.conv3d(torch.nn.functional.pad(vol, (2,) * 6, mode="replicate"), w)
+    ref = torch.cat([torch.zeros_like(ref[:, :, :1]), ref[:, :, 1:]], dim=2)
+    got = plan.laplacian(vol.detach().view(C, 1, M, N, N), adjoint=False)
+    assert O.rel_l2(got.cpu(), ref.detach().cpu()) <= 2e-6
+    assert torch.count_nonzero(got[:, :, 0]) == 0
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    gv = plan.laplacian(g, adjoint=True)
+    assert O.rel_l2(gv.cpu(), vol.grad.cpu()) <= 2e-6
+
+
 @pytest.mark.parametrize("M,N,method", [(64, 16, "lct"), (128, 64, "lct"), (64, 128, "lct"), (64, 32, "bp")])
 def test_device_built_filter_matches_host_built(M, N, method, monkeypatch):
     """Row f3: the filter built on the GPU from the PSF support gives the same volumes as the one built on
