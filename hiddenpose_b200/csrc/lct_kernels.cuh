@@ -34,6 +34,9 @@
 #include "lct_fft.cuh"
 #include "lct_tables.h"
 
+#ifndef LCT_TIME_PRELOAD
+#define LCT_TIME_PRELOAD 1      // the persistent K1 requests its tables and first tile from the kernel driver
+#endif
 #ifndef LCT_K1_BLOCKS_256
 #define LCT_K1_BLOCKS_256 4      // blocks per SM the 256-thread time kernels (M = 128) are compiled for (4: 64 registers)
 #endif
@@ -603,6 +606,19 @@ template <class P, int CT_> struct TimeFwdPersistent {
     static constexpr bool kHasPrologue = true;
     static LCT_DEV void prologue(const Params&, Regs&, unsigned char* smem, int tid, int, int) { TwS::fill(smem, tid, kThreads); }
 
+    // the operator tables and the block's first tile are requested from the kernel driver, right after the wait for the
+    // previous kernel and before the prologue's barrier: the first phase is then the same code for every tile of the walk
+    // (K1 229 -> 221 us at cfg3, 122 -> 119 at cfg5)
+    static constexpr bool kPreload = LCT_TIME_PRELOAD && kPersist;
+    static LCT_DEV void preload(const Params& p, Regs&, unsigned char* smem_base, int tid, int bx, int) {
+        if constexpr (kPreload) {
+            unsigned char* smem = smem_base + TwS::kBytes;
+            for (int j = tid; j < M + kLongRows; j += kThreads)
+                reinterpret_cast<float4*>(smem + kWork)[j] = j < M ? LCT_LDG(p.pair + j) : LCT_LDG(p.ell + (j - M));
+            issue_tile(p, smem, tid, bx);
+        }
+    }
+
     // x tile -> xs[(M+2)][CT] f32 by 16-byte asynchronous copies, zero-filled outside the window [be, en) and in
     // the two pad rows.  Slot i = tid + u * kThreads covers row i / V4, column quad i % V4: the quad is fixed per
     // thread and the row advances by kThreads / V4 per slot, so the source offset is stepped, not recomputed.
@@ -645,7 +661,7 @@ template <class P, int CT_> struct TimeFwdPersistent {
         float* xs = reinterpret_cast<float*>(smem);
         float2* zs = reinterpret_cast<float2*>(smem + kXs);
         if constexpr (PH == 0 && kPersist) {
-            if (it == 0) {
+            if (!kPreload && it == 0) {
                 for (int j = tid; j < M + kLongRows; j += kThreads)
                     reinterpret_cast<float4*>(smem + kWork)[j] = j < M ? LCT_LDG(p.pair + j) : LCT_LDG(p.ell + (j - M));
                 issue_tile(p, smem, tid, tile);
@@ -799,6 +815,8 @@ template <class P, int CT_> struct TimeInv {
         for (int k = tid; k <= M; k += kThreads) bulk_load(smem + (size_t)k * kRowBytes, src + (size_t)k * NN, kRowBytes, bar);
     }
 
+    // (Requesting the row records and the first tile from the kernel driver instead of in the first phase, as the
+    //  persistent K1 does, measured slower here: 37.3 -> 39.4 us at cfg2, 216 -> 219 at cfg3.)
     // spectrum tile -> zs[(M+1)][CT] c64 by 16-byte asynchronous copies (two columns each)
     static LCT_DEV void issue_tile(const Params& p, unsigned char* smem, int tid, int tile) {
         if constexpr (kBulk) { issue_tile_bulk(p, smem, tid, tile); return; }
