@@ -1206,7 +1206,8 @@ template <int N> LCT_DEV int sym_twist(int k) { return k <= N ? 0 : k; }
 // Two-stage plans only (lanes run along the line so global accesses coalesce).
 // ---------------------------------------------------------------------------
 // (An instantiation without the channel loop for single-channel launches, as the H-axis kernels have it, measured slower:
-//  416 vs 408 us at 512x256^2, 123 vs 119 us at 1 x 512x128^2.)
+//  416 vs 408 us at 512x256^2, 123 vs 119 us at 1 x 512x128^2.  Channel 0's row requested before the prologue barrier, as
+//  in the plane kernel: no difference here, 430 vs 408 us in the parity-split kernel at one channel.)
 template <class P, int RB_, bool SYM = false> struct ColFilter {
     static_assert(P::S == 2, "ColFilter needs a two-stage plan");
     static_assert(32 % P::TL == 0, "the threads of one line must share a warp");
