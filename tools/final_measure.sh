@@ -7,7 +7,9 @@ out=gpurun_out
 mkdir -p $out
 python -m pytest tests -x -q -m gpu > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest_gpu.log
 python __graft_entry__.py smoke > $out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" >> $out/${tag}_smoke.log
+t0=$(date +%s)
 python bench.py --steps 20 --warmup 5 > $out/${tag}_bench_cfg2.json 2> $out/${tag}_bench_cfg2.err
+echo "bench.py --steps 20 --warmup 5: wall $(( $(date +%s) - t0 )) s" > $out/${tag}_bench_cfg2.time
 for w in cfg1 cfg3 cfg4 cfg5; do
   python bench.py --steps 20 --warmup 5 --workload $w --no-strong --no-train > $out/${tag}_bench_$w.json 2> $out/${tag}_bench_$w.err
 done
