@@ -37,6 +37,9 @@
 #ifndef LCT_TIME_PRELOAD
 #define LCT_TIME_PRELOAD 1      // the persistent K1 requests its tables and first tile from the kernel driver
 #endif
+#ifndef LCT_K1_ASYNC_TILE_256
+#define LCT_K1_ASYNC_TILE_256 1
+#endif
 #ifndef LCT_K1_BLOCKS_256
 #define LCT_K1_BLOCKS_256 4      // blocks per SM the 256-thread time kernels (M = 128) are compiled for (4: 64 registers)
 #endif
@@ -494,13 +497,23 @@ template <class P, int CT_> struct TimeFwd {
             const int t0 = tid / V4;
             ptrdiff_t off = (ptrdiff_t)(t0 - be) * (NN / 4) + tid % V4;
             const ptrdiff_t off_step = (ptrdiff_t)kRowStep * (NN / 4);
-            float4 v[kIters];
+            // M = 256: the tile goes straight into shared memory by 16-byte asynchronous copies (no staging registers, no
+            // stores: K1 39.0 -> 36.9 us at 8 x 256x64^2, 115 -> 108 at 32); at M = 128 and M = 64 the loads through
+            // registers are faster (90 vs 96 us at 16 x 128^3, 14.5 vs 16.4 at 8 x 64x64^2)
+            constexpr bool kAsyncTile = LCT_K1_ASYNC_TILE_256 && M == 256;
+            [[maybe_unused]] float4 v[kIters];
             LCT_UNROLL
             for (int u = 0; u < kIters; ++u, off += off_step) {
                 const int t = t0 + u * kRowStep;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t >= be && t < en) v[u] = LCT_LDG(src + off);
+                const bool ok = t >= be && t < en;
+                if constexpr (kAsyncTile) {                  // zero-filled outside the window
+                    if (tid + u * kThreads < kSlots) cp_async16(xs4 + tid + u * kThreads, ok ? src + off : src, ok);
+                } else {
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) v[u] = LCT_LDG(src + off);
+                }
             }
+            if constexpr (kAsyncTile) cp_async_commit();
             if (p.ahead > 0) {
                 // own loads are in flight: ask L2 for the tile of the block that will run here about one block life later
                 const int gx = NN / CT;
@@ -511,10 +524,13 @@ template <class P, int CT_> struct TimeFwd {
                     for (int t = tid; t < p.in_T; t += kThreads) prefetch_l2(ns + (size_t)t * NN);
                 }
             }
-            LCT_UNROLL
-            for (int u = 0; u < kIters; ++u) {
-                const int i = tid + u * kThreads;
-                if (i < kSlots) xs4[i] = v[u];
+            if constexpr (kAsyncTile) cp_async_wait_all();
+            else {
+                LCT_UNROLL
+                for (int u = 0; u < kIters; ++u) {
+                    const int i = tid + u * kThreads;
+                    if (i < kSlots) xs4[i] = v[u];
+                }
             }
         } else if constexpr (PH == 1) {
             fwd_stage<P, 0, true, TwS>(tau,
