@@ -808,6 +808,9 @@ template <class P, int CT_> struct TimeInv {
         TwS::fill(smem, tid, kThreads);
         if (tid == 0) minmax_slot_init(reinterpret_cast<MinMaxSlot*>(smem + TwS::kBytes + kWork + (size_t)M * sizeof(float4)));
         if (kBulk && tid == 0) mbar_init(reinterpret_cast<unsigned long long*>(smem + TwS::kBytes + kBarRel), 1);
+#ifndef LCT_EMULATE
+        if constexpr (kBulk) __syncthreads();               // the driver skips the barrier behind a table-less prologue
+#endif
     }
 
 #ifndef LCT_TIME_INV_BULK
@@ -1723,6 +1726,9 @@ template <class PHp, class PWp, int NT_, bool PERSIST = false> struct PlaneFilte
 template <class K, class = void> struct has_prologue { static constexpr bool value = false; };
 template <class K> struct has_prologue<K, decltype((void)K::kHasPrologue)> { static constexpr bool value = true; };
 
+template <class K, class = void> struct prologue_is_empty { static constexpr bool value = false; };
+template <class K> struct prologue_is_empty<K, std::enable_if_t<(K::TwS::kBytes == 0)>> { static constexpr bool value = true; };
+
 template <class K, class = void> struct has_preload { static constexpr bool value = false; };
 template <class K> struct has_preload<K, decltype((void)K::kPreload)> { static constexpr bool value = true; };
 
@@ -1760,7 +1766,12 @@ template <class K> __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks)
     asm volatile("griddepcontrol.wait;" ::: "memory");                   // no-op for a plain launch
     if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if constexpr (has_preload<K>::value) K::preload(p, r, smem, threadIdx.x, blockIdx.x, blockIdx.y);    // loads fly across the barrier
-    if constexpr (has_prologue<K>::value) __syncthreads();
+#ifndef LCT_SKIP_EMPTY_PROLOGUE_BARRIER
+#define LCT_SKIP_EMPTY_PROLOGUE_BARRIER 1
+#endif
+    // kernels whose prologue fills no table (constant-bank twiddles) have nothing to publish before phase 0; whatever
+    // else the prologue initialises is first used behind a later phase barrier
+    if constexpr (has_prologue<K>::value && !(LCT_SKIP_EMPTY_PROLOGUE_BARRIER && prologue_is_empty<K>::value)) __syncthreads();
     if constexpr (has_single_pass<K>::value) {
         PhaseLoop<K, 0>::run(p, r, smem, 0);                 // no loop: nothing in Regs outlives its last use
     } else {
