@@ -63,6 +63,7 @@ struct TwGlobal : TwConst {
     static inline void fill(unsigned char*, int, int) {}
 };
 #define LCT_LDG(p) (*(p))
+#define LCT_LDCG(p) (*(p))
 #else
 __constant__ float2 c_tw[kTwN];          // exp(-2*pi*i*j/1024), built in double on the host
 __device__ float2 g_tw[kTwN];            // same table in global memory for lane-divergent lookups
@@ -84,6 +85,7 @@ struct TwGlobal {
     template <int Ls, int STR> static LCT_DEV float2 stage_mulc(float2 a, int k, int lo) { return mulc(a, (k * lo) * (kTwN / Ls)); }
 };
 #define LCT_LDG(p) __ldg(p)
+#define LCT_LDCG(p) __ldcg(p)           // L2 only: a line that is read once has no use for L1
 #endif
 
 // Constant-bank twiddles behind the same interface as TwShared (no table, nothing to fill).
@@ -1004,7 +1006,7 @@ template <class P, int CT_> struct RowFwd {
         float2* zs = reinterpret_cast<float2*>(smem);
         const float2* src = p.s1 + (size_t)by * N * N + bx * CT + col;
         float2* dst = p.s2 + (size_t)by * L * N + bx * CT + col;
-        auto ld_g = [&](int pos, int) { return src[(size_t)pos * N]; };
+        auto ld_g = [&](int pos, int) { return LCT_LDCG(src + (size_t)pos * N); };        // (K2 156 -> 155 us at cfg4)
         auto ld_s = [&](int pos, int) { return zs[pos * CT + col]; };
         auto st_s = [&](int pos, int, float2 v) { zs[pos * CT + col] = v; };
         auto st_g = [&](int pos, int slot, float2 v) { dst[(size_t)P::template freq_of<P::S - 1>(pos, slot) * N] = v; };
@@ -1057,7 +1059,8 @@ template <class P, int CT_> struct RowInv {
         float2* zs = reinterpret_cast<float2*>(smem);
         const float2* src = p.s2 + (size_t)by * L * N + bx * CT + col;
         float2* dst = p.s1 + (size_t)by * N * N + bx * CT + col;
-        auto ld_g = [&](int pos, int slot) { return src[(size_t)P::template freq_of<P::S - 1>(pos, slot) * N]; };
+        // L2-only loads: K4 246 -> 242 us at cfg3, 133 -> 131 at cfg4
+        auto ld_g = [&](int pos, int slot) { return LCT_LDCG(src + (size_t)P::template freq_of<P::S - 1>(pos, slot) * N); };
         auto ld_s = [&](int pos, int) { return zs[pos * CT + col]; };
         auto st_s = [&](int pos, int, float2 v) { zs[pos * CT + col] = v; };
         auto st_g = [&](int pos, int, float2 v) { dst[(size_t)pos * N] = v; };
@@ -1188,7 +1191,7 @@ template <class P, int CT_> struct RowInvSplit {
                     }
                 }
                 inv_stage<P, 1, false, TwS>(tau,
-                    [&](int pos, int slot) { return src[(size_t)P::template freq_of<1>(pos, slot) * (2 * N)]; }, st_s);
+                    [&](int pos, int slot) { return LCT_LDCG(src + (size_t)P::template freq_of<1>(pos, slot) * (2 * N)); }, st_s);
             } else {
                 inv_stage<P, 0, false, TwS>(tau, ld_s, st_s);       // in place: a butterfly writes the positions it read
             }
