@@ -85,7 +85,9 @@ struct TwGlobal {
     template <int Ls, int STR> static LCT_DEV float2 stage_mulc(float2 a, int k, int lo) { return mulc(a, (k * lo) * (kTwN / Ls)); }
 };
 #define LCT_LDG(p) __ldg(p)
-#define LCT_LDCG(p) __ldcg(p)           // L2 only: a line that is read once has no use for L1
+#define LCT_LDCG(p) __ldcg(p)           // L2 only: a line that is read once has no use for L1 (measured per kernel: it pays in
+                                        // the H-axis kernels, changes nothing in the plane kernel; evict-first stores (__stcs) of
+                                        // K5's output made that kernel 18 % slower at M = 128 and changed nothing elsewhere)
 #endif
 
 // Constant-bank twiddles behind the same interface as TwShared (no table, nothing to fill).
