@@ -634,7 +634,7 @@ def main():
         streamer = hp.LctStreamer(layer, tbes, tens, depth=2)
         streamer.run([x_hosts[i % n_buf] for i in range(W)], [y_hosts[i % n_buf] for i in range(W)])
         e2e_runs = []
-        for _ in range(11):                     # host-side jitter (other tenants on the PCIe switch) comes in bursts of several runs: median of 11
+        for _ in range(21):                     # host-side jitter (other tenants on the PCIe switch) comes in bursts of several runs: median of 21
             barrier()
             t0 = time.perf_counter()
             streamer.run([x_hosts[i % n_buf] for i in range(K)], [y_hosts[i % n_buf] for i in range(K)])
@@ -650,7 +650,7 @@ def main():
         scratch_y = torch.empty_like(y)
         c_in, c_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         link_runs = []
-        for _ in range(5):
+        for _ in range(9):
             barrier()
             t0 = time.perf_counter()
             for i in range(K):
@@ -673,7 +673,7 @@ def main():
                "host_bound_to_gpu_numa_node": numa_bound, "host_topology": host_topology(local_rank),
                "how": "LctStreamer public API: pinned x -> H2D -> lct.forward -> D2H of the whole volume for every "
                       "step; upload/transform/download of consecutive steps overlap on three streams; host wall "
-                      "clock from first upload to last byte landed; median of 11 runs of K steps",
+                      "clock from first upload to last byte landed; median of 21 runs of K steps",
                "runs_ms": e2e_runs}
 
     # ---- the BASELINE-named multi-GPU configurations, on every line (bounded: K_side steps each) ----------
